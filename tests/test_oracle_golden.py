@@ -1,0 +1,119 @@
+"""Pin the CPU oracle (oracle/x3d_oracle.py) against outputs of the reference itself.
+
+tests/golden/*.npz were produced by oracle/make_golden.py, which imports the
+unmodified /root/reference/x3d.py and runs it in fp64.  No GPU needed.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import x3d_oracle as O
+from oracle.make_golden import CASES
+
+REF = '/root/reference'
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+def _run_oracle(case, conv_impl):
+    c = CASES[case]
+    sd = O.make_state_dict(c['version'], c['n_classes'], c['splits'])
+    x = O.det_clip(c['shape'])
+    gold = np.load(os.path.join(GOLDEN, case + '.npz'))
+    labels = torch.from_numpy(gold['labels'])
+    logits, loss, grads, stats = O.loss_and_grads(sd, x, labels, version=c['version'], splits=c['splits'],
+                                                  training=True, task=c['task'], conv_impl=conv_impl)
+    return gold, sd, x, logits, loss, grads, stats
+
+
+@pytest.mark.parametrize('case,conv_impl', [('s_small_split2', 'explicit'), ('s_small_split2', 'aten'),
+                                            ('m_odd_loc', 'explicit'), ('m_odd_loc', 'aten')])
+def test_oracle_matches_reference_golden(case, conv_impl):
+    gold, sd, x, logits, loss, grads, stats = _run_oracle(case, conv_impl)
+    assert _rel(logits.numpy(), gold['logits']) < 1e-10
+    assert abs(loss.item() - float(gold['loss'])) < 1e-10
+    for k, g in grads.items():
+        # fp64 noise floor of whole-network grads through train-mode BN is ~1e-9
+        assert _rel(g.reshape(-1)[:16].numpy(), gold['ghead/' + k]) < 1e-6, k
+        assert abs(g.norm().item() - float(gold['gnorm/' + k])) <= 1e-6 * float(gold['gnorm/' + k]) + 1e-12, k
+    for k in gold.files:
+        if k.startswith('gfull/'):
+            assert _rel(grads[k[6:]].numpy(), gold[k]) < 1e-6, k
+        if k.startswith('stat/'):
+            assert _rel(stats[k[5:]].numpy(), gold[k]) < 1e-10, k
+
+
+def test_oracle_eval_and_aggregate():
+    case = 's_small_split2'
+    c = CASES[case]
+    gold, sd, x, logits, loss, grads, stats = _run_oracle(case, 'explicit')
+    sd2 = dict(sd)
+    sd2.update(stats)
+    for k in list(sd2):
+        if k.endswith('split_bn.running_mean'):
+            p = k[:-len('.split_bn.running_mean')]
+            m, v = O.aggregate_stats(sd2[k], sd2[p + '.split_bn.running_var'], c['splits'])
+            sd2[p + '.bn.running_mean'], sd2[p + '.bn.running_var'] = m, v
+    for k in gold.files:
+        if k.startswith('agg/'):
+            assert _rel(sd2[k[4:]].numpy(), gold[k]) < 1e-12, k
+    with torch.no_grad():
+        ev = O.forward(sd2, x, version=c['version'], splits=c['splits'], training=False, task=c['task'])
+    assert _rel(ev.numpy(), gold['eval_logits']) < 1e-10
+
+
+@pytest.mark.slow
+def test_oracle_config1_logits():
+    """BASELINE config 1 (X3D-S, B=2, 13x160x160): forward only, aten convs (fast)."""
+    c = CASES['s_config1']
+    gold = np.load(os.path.join(GOLDEN, 's_config1.npz'))
+    sd = O.make_state_dict(c['version'], c['n_classes'], c['splits'])
+    x = O.det_clip(c['shape'])
+    with torch.no_grad():
+        logits = O.forward(sd, x, version='S', splits=1, training=True, conv_impl='aten')
+    assert _rel(logits.numpy(), gold['logits']) < 1e-10
+
+
+def test_manifest_matches_reference():
+    with open(os.path.join(GOLDEN, 'state_dict_manifest.json')) as f:
+        man = json.load(f)
+    for v in ('S', 'M', 'XL'):
+        for s in (1, 2, 4, 8):
+            mine = [[k, list(shp), dt] for k, shp, dt in O.state_dict_manifest(v, 400, s)]
+            assert mine == man[f'{v}_s{s}'], (v, s)
+    mine = [[k, list(shp), dt] for k, shp, dt in O.state_dict_manifest('M', 157, 1)]
+    assert mine == man['M_loc157']
+    assert len(man['M_s4']) == 820 and len(man['XL_s1']) == 1659
+
+
+def test_multigrid_shape_law():
+    """SURVEY.md A3 / log lines 15,82,158,234 (global batch 128, T0=8, crop 224)."""
+    t = O.multigrid_shapes(128, 8, 224)
+    assert t[0] == [(2048, 2, 111), (1024, 2, 158)]
+    assert t[1] == [(1024, 4, 111), (512, 4, 158)]
+    assert t[2] == [(1024, 4, 112), (512, 4, 158), (256, 4, 224)]
+    assert t[3] == [(512, 8, 112), (256, 8, 158), (128, 8, 224)]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present on this machine')
+def test_oracle_matches_live_reference_block():
+    """Live check against the reference module itself (build container only)."""
+    sys.path.insert(0, REF)
+    import x3d as ref
+    torch.manual_seed(0)
+    m = ref.generate_model('S', n_classes=11, dropout=0.0, base_bn_splits=2).double()
+    sd = O.det_fill_state_dict(m.state_dict())
+    m.load_state_dict(sd)
+    m.train()
+    x = O.det_clip((4, 3, 3, 20, 24))
+    got = O.forward(sd, x, version='S', splits=2, training=True)
+    assert _rel(got.detach().numpy(), m(x).detach().numpy()) < 1e-10
