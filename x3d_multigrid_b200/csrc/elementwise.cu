@@ -1,0 +1,1023 @@
+// Bandwidth-bound elementwise / reduction kernels of the X3D hot path:
+// layout converters, parameter repack, split-BN finalize / apply / backward, Swish + SE gate,
+// head pooling.  All activation tensors are [N][P][Cp] (NDHWC, Cp % 8 == 0), accessed with
+// 16-byte vectors; block = (channel vectors) x (position rows), grid = (chunks, N).
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace x3d {
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace x3d
+
+using namespace x3d;
+
+extern "C" const char* x3d_last_error(void) { return x3d::g_err; }
+extern "C" int x3d_abi_version(void) { return 1; }
+extern "C" int64_t x3d_launch_count(void) { return x3d::g_launches.load(); }
+
+#define ROW_PROLOGUE()                                    \
+  constexpr int VEC = Vec<T>::N;                          \
+  const int n = blockIdx.y;                               \
+  const int cvec = threadIdx.x % cv;                      \
+  const int prow = threadIdx.x / cv;                      \
+  const int64_t p0 = (int64_t)blockIdx.x * chunk;         \
+  const int64_t p1 = (p0 + chunk < P) ? p0 + chunk : P;   \
+  const int c0 = cvec * VEC;                              \
+  (void)c0
+
+// =======================================================================================
+// layout converters
+// =======================================================================================
+// src NCDHW fp32 -> dst NDHWC T with Cp lanes.  32x32 smem transpose over (c, spatial).
+template <typename T>
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int Cp,
+                                      int64_t S /*T*H*W*/) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t s0 = (int64_t)blockIdx.x * 32;
+  const int cb = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = cb + i;
+    int64_t s = s0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && s < S) ? src[((int64_t)n * C + c) * S + s] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t s = s0 + i;
+    int c = cb + threadIdx.x;
+    if (s < S && c < Cp) dst[((int64_t)n * S + s) * Cp + c] = from_float<T>(tile[threadIdx.x][i]);
+  }
+}
+template <typename T>
+__global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int Cp,
+                                      int64_t S) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t s0 = (int64_t)blockIdx.x * 32;
+  const int cb = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t s = s0 + i;
+    int c = cb + threadIdx.x;
+    tile[i][threadIdx.x] = (s < S && c < C) ? to_float<T>(src[((int64_t)n * S + s) * Cp + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = cb + i;
+    int64_t s = s0 + threadIdx.x;
+    if (c < C && s < S) dst[((int64_t)n * C + c) * S + s] = tile[threadIdx.x][i];
+  }
+}
+
+extern "C" int x3d_ncdhw_to_ndhwc(const float* src, void* dst, int64_t N, int64_t C, int64_t Cp, int64_t T_,
+                                  int64_t H, int64_t W, x3d_dtype_t dt, x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0 && Cp >= C, "Cp must be a multiple of 8 and >= C");
+  int64_t S = T_ * H * W;
+  if (N * S == 0) return 0;
+  dim3 grid((unsigned)cdiv(S, 32), (unsigned)cdiv(Cp, 32), (unsigned)N), block(32, 8);
+  X3D_DISPATCH_DTYPE(dt, (ncdhw_to_ndhwc_kernel<T><<<grid, block, 0, as_stream(stream)>>>(src, (T*)dst, (int)C, (int)Cp, S)));
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int x3d_ndhwc_to_ncdhw(const void* src, float* dst, int64_t N, int64_t C, int64_t Cp, int64_t T_,
+                                  int64_t H, int64_t W, x3d_dtype_t dt, x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0 && Cp >= C, "Cp must be a multiple of 8 and >= C");
+  int64_t S = T_ * H * W;
+  if (N * S == 0) return 0;
+  dim3 grid((unsigned)cdiv(S, 32), (unsigned)cdiv(C, 32), (unsigned)N), block(32, 8);
+  X3D_DISPATCH_DTYPE(dt, (ndhwc_to_ncdhw_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)src, dst, (int)C, (int)Cp, S)));
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// =======================================================================================
+// parameter repack (one launch for the whole network)
+// =======================================================================================
+__global__ void pack_params_kernel(const x3d_pack_desc_t* __restrict__ descs) {
+  const x3d_pack_desc_t d = descs[blockIdx.y];
+  const int64_t total = (int64_t)d.dst_rows * d.dst_cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int dr = (int)(i / d.dst_cols), dc = (int)(i % d.dst_cols);
+    int r = d.transpose ? dc : dr;
+    int c = d.transpose ? dr : dc;
+    float v = (r < d.rows && c < d.cols) ? d.src[(int64_t)r * d.cols + c] : 0.f;
+    if (d.dtype == X3D_BF16)
+      reinterpret_cast<__nv_bfloat16*>(d.dst)[i] = __float2bfloat16_rn(v);
+    else
+      reinterpret_cast<float*>(d.dst)[i] = v;
+  }
+}
+extern "C" int x3d_pack_params(const x3d_pack_desc_t* descs_dev, int n_desc, int64_t max_dst_elems,
+                               x3d_stream_t stream) {
+  if (n_desc == 0) return 0;
+  int64_t bx = cdiv(max_dst_elems, 256);
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  pack_params_kernel<<<dim3((unsigned)bx, (unsigned)n_desc), 256, 0, as_stream(stream)>>>(descs_dev);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// =======================================================================================
+// split-BN finalize: per-sample sums -> per-(split,channel) scale/shift + running stats
+// =======================================================================================
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int splits, double P, int C, int Cp,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ run_mean, float* __restrict__ run_var,
+                                   int64_t* __restrict__ nbt, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0 && nbt) *nbt += 1;
+  if (idx >= splits * Cp) return;
+  const int b = idx / Cp, c = idx % Cp;
+  if (c >= C) {
+    scale[idx] = 0.f; shift[idx] = 0.f; mean_o[idx] = 0.f; rstd_o[idx] = 0.f;
+    return;
+  }
+  double s1 = 0.0, s2 = 0.0;
+  for (int n = b; n < N; n += splits) {
+    s1 += stats[((int64_t)n * Cp + c) * 2 + 0];
+    s2 += stats[((int64_t)n * Cp + c) * 2 + 1];
+  }
+  const double m = (double)(N / splits) * P;
+  const double mu = s1 / m;
+  double var = s2 / m - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const double r = 1.0 / sqrt(var + (double)eps);
+  const float sc = (float)((double)gamma[c] * r);
+  scale[idx] = sc;
+  shift[idx] = (float)((double)beta[c] - mu * (double)gamma[c] * r);
+  mean_o[idx] = (float)mu;
+  rstd_o[idx] = (float)r;
+  if (run_mean) {
+    const int ri = b * C + c;  // x3d.py:50: channel index of the (n//s, c*s) view is b*C + c
+    const double unb = m > 1.0 ? var * m / (m - 1.0) : var;
+    run_mean[ri] = (float)((1.0 - momentum) * (double)run_mean[ri] + momentum * mu);
+    run_var[ri] = (float)((1.0 - momentum) * (double)run_var[ri] + momentum * unb);
+  }
+}
+extern "C" int x3d_bn_finalize(const double* stats, int64_t N, int splits, int64_t P, int64_t C, int64_t Cp,
+                               const float* gamma, const float* beta, float* run_mean, float* run_var,
+                               int64_t* nbt, float momentum, float eps, float* scale, float* shift,
+                               float* mean, float* rstd, x3d_stream_t stream) {
+  X3D_CHECK_ARG(splits >= 1 && N % splits == 0, "batch must be divisible by num_splits (x3d.py:50)");
+  int total = (int)(splits * Cp);
+  bn_finalize_kernel<<<(unsigned)cdiv(total, 128), 128, 0, as_stream(stream)>>>(
+      stats, (int)N, splits, (double)P, (int)C, (int)Cp, gamma, beta, run_mean, run_var, nbt, momentum, eps, scale,
+      shift, mean, rstd);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void bn_eval_params_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, int C, int Cp,
+                                      float eps, float* scale, float* shift, float* mean, float* rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  float sc = 0.f, sh = 0.f, mu = 0.f, r = 0.f;
+  if (c < C) {
+    r = (float)(1.0 / sqrt((double)rv[c] + (double)eps));
+    mu = rm[c];
+    sc = gamma[c] * r;
+    sh = beta[c] - mu * sc;
+  }
+  scale[c] = sc; shift[c] = sh;
+  if (mean) mean[c] = mu;
+  if (rstd) rstd[c] = r;
+}
+extern "C" int x3d_bn_eval_params(const float* gamma, const float* beta, const float* run_mean,
+                                  const float* run_var, int64_t C, int64_t Cp, float eps, float* scale,
+                                  float* shift, float* mean, float* rstd, x3d_stream_t stream) {
+  bn_eval_params_kernel<<<(unsigned)cdiv(Cp, 128), 128, 0, as_stream(stream)>>>(gamma, beta, run_mean, run_var, (int)C,
+                                                                            (int)Cp, eps, scale, shift, mean, rstd);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// =======================================================================================
+// out = [relu](a*scale+shift [+ res | + res*rs+rh])
+// =======================================================================================
+template <typename T, int RES /*0 none, 1 raw, 2 affine*/, bool RELU>
+__global__ void bn_act_fwd_kernel(const T* __restrict__ a, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, int splits, const T* __restrict__ res,
+                                  const float* __restrict__ rscale, const float* __restrict__ rshift,
+                                  T* __restrict__ out, int64_t P, int Cp, int cv, int rows, int64_t chunk) {
+  ROW_PROLOGUE();
+  const int b = n % splits;
+  float sc[VEC], sh[VEC], rs[VEC], rh[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    sc[j] = scale[b * Cp + c0 + j];
+    sh[j] = shift[b * Cp + c0 + j];
+    rs[j] = RES == 2 ? rscale[b * Cp + c0 + j] : 1.f;
+    rh[j] = RES == 2 ? rshift[b * Cp + c0 + j] : 0.f;
+  }
+  for (int64_t p = p0 + prow; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float v[VEC], r[VEC];
+    load_vec<T>(a + off, v);
+    if (RES) load_vec<T>(res + off, r);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float y = fmaf(v[j], sc[j], sh[j]);
+      if (RES == 1) y += r[j];
+      if (RES == 2) y += fmaf(r[j], rs[j], rh[j]);
+      if (RELU) y = fmaxf(y, 0.f);
+      v[j] = y;
+    }
+    store_vec<T>(out + off, v);
+  }
+}
+
+extern "C" int x3d_bn_act_fwd(const void* a, const float* scale, const float* shift, int splits,
+                              const void* res, const float* res_scale, const float* res_shift, int relu,
+                              void* out, int64_t N, int64_t P, int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0, "Cp % 8");
+  if (N * P == 0) return 0;
+  const int mode = res ? (res_scale ? 2 : 1) : 0;
+#define LAUNCH_(M, R)                                                                                          \
+  bn_act_fwd_kernel<T, M, R><<<grid, g.threads, 0, as_stream(stream)>>>((const T*)a, scale, shift, splits,      \
+                                                                         (const T*)res, res_scale, res_shift,  \
+                                                                         (T*)out, P, (int)Cp, g.cv, g.rows, g.chunk)
+  X3D_DISPATCH_DTYPE(dt, {
+    RowGeom g = make_row_geom<T>(N, P, Cp, 8 * kNumSMs);
+    dim3 grid(g.chunks, (unsigned)N);
+    if (mode == 0 && relu) LAUNCH_(0, true);
+    else if (mode == 0) LAUNCH_(0, false);
+    else if (mode == 1 && relu) LAUNCH_(1, true);
+    else if (mode == 1) LAUNCH_(1, false);
+    else if (relu) LAUNCH_(2, true);
+    else LAUNCH_(2, false);
+  });
+#undef LAUNCH_
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// =======================================================================================
+// BN backward
+// =======================================================================================
+template <typename T, bool MASK>
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ mask_out,
+                                     const T* __restrict__ a, double* __restrict__ stats, int64_t P, int Cp, int cv,
+                                     int rows, int64_t chunk) {
+  extern __shared__ float s_acc[];
+  ROW_PROLOGUE();
+  float a0[VEC], a1[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) a0[j] = a1[j] = 0.f;
+  for (int64_t p = p0 + prow; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float d[VEC], x[VEC], m[VEC];
+    load_vec<T>(dout + off, d);
+    load_vec<T>(a + off, x);
+    if (MASK) load_vec<T>(mask_out + off, m);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float dp = (!MASK || m[j] > 0.f) ? d[j] : 0.f;
+      a0[j] += dp;
+      a1[j] = fmaf(dp, x[j], a1[j]);
+    }
+  }
+  block_stats_flush<VEC>(a0, a1, cvec, Cp, s_acc, stats + (int64_t)n * Cp * 2);
+}
+extern "C" int x3d_bn_bwd_reduce(const void* dout, const void* mask_out, const void* a, double* stats,
+                                 int64_t N, int64_t P, int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0, "Cp % 8");
+  if (N * P == 0) return 0;
+  X3D_DISPATCH_DTYPE(dt, {
+    RowGeom g = make_row_geom<T>(N, P, Cp);
+    dim3 grid(g.chunks, (unsigned)N);
+    size_t smem = Cp * 2 * sizeof(float);
+    if (mask_out)
+      bn_bwd_reduce_kernel<T, true><<<grid, g.threads, smem, as_stream(stream)>>>(
+          (const T*)dout, (const T*)mask_out, (const T*)a, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
+    else
+      bn_bwd_reduce_kernel<T, false><<<grid, g.threads, smem, as_stream(stream)>>>(
+          (const T*)dout, nullptr, (const T*)a, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
+  });
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// coefficients: da = A*dpre + B*a + Cc.  One thread per channel, loops splits and samples.
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int N, int splits, double P, int C, int Cp,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, int train, float* __restrict__ coef,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  const int sC = splits * Cp;
+  if (c >= C) {
+    for (int b = 0; b < splits; ++b) {
+      coef[0 * sC + b * Cp + c] = 0.f; coef[1 * sC + b * Cp + c] = 0.f; coef[2 * sC + b * Cp + c] = 0.f;
+    }
+    return;
+  }
+  const double g = gamma[c];
+  const double m = (double)(N / splits) * P;
+  double dg = 0.0, db = 0.0;
+  for (int b = 0; b < splits; ++b) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int n = b; n < N; n += splits) {
+      s1 += stats[((int64_t)n * Cp + c) * 2 + 0];
+      s2 += stats[((int64_t)n * Cp + c) * 2 + 1];
+    }
+    const double mu = mean[b * Cp + c], r = rstd[b * Cp + c];
+    const double sxh = (s2 - mu * s1) * r;  // sum dpre * xhat
+    dg += sxh;
+    db += s1;
+    double A = g * r, B = 0.0, Cc = 0.0;
+    if (train) {
+      const double m1 = s1 / m, m2 = sxh / m;
+      B = -g * r * r * m2;
+      Cc = g * r * (-m1 + mu * r * m2);
+    }
+    coef[0 * sC + b * Cp + c] = (float)A;
+    coef[1 * sC + b * Cp + c] = (float)B;
+    coef[2 * sC + b * Cp + c] = (float)Cc;
+  }
+  if (dgamma) dgamma[c] += (float)dg;
+  if (dbeta) dbeta[c] += (float)db;
+}
+extern "C" int x3d_bn_bwd_finalize(const double* stats, int64_t N, int splits, int64_t P, int64_t C, int64_t Cp,
+                                   const float* gamma, const float* mean, const float* rstd, int train,
+                                   float* coef, float* dgamma, float* dbeta, x3d_stream_t stream) {
+  bn_bwd_finalize_kernel<<<(unsigned)cdiv(Cp, 64), 64, 0, as_stream(stream)>>>(stats, (int)N, splits, (double)P, (int)C,
+                                                                            (int)Cp, gamma, mean, rstd, train, coef,
+                                                                            dgamma, dbeta);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, bool MASK>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ mask_out,
+                                    const T* __restrict__ a, const float* __restrict__ coef, int splits,
+                                    T* __restrict__ da, int64_t P, int Cp, int cv, int rows, int64_t chunk) {
+  ROW_PROLOGUE();
+  const int b = n % splits;
+  const int sC = splits * Cp;
+  float A[VEC], B[VEC], Cc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    A[j] = coef[0 * sC + b * Cp + c0 + j];
+    B[j] = coef[1 * sC + b * Cp + c0 + j];
+    Cc[j] = coef[2 * sC + b * Cp + c0 + j];
+  }
+  for (int64_t p = p0 + prow; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float d[VEC], x[VEC], m[VEC];
+    load_vec<T>(dout + off, d);
+    load_vec<T>(a + off, x);
+    if (MASK) load_vec<T>(mask_out + off, m);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float dp = (!MASK || m[j] > 0.f) ? d[j] : 0.f;
+      d[j] = fmaf(A[j], dp, fmaf(B[j], x[j], Cc[j]));
+    }
+    store_vec<T>(da + off, d);
+  }
+}
+extern "C" int x3d_bn_bwd_apply(const void* dout, const void* mask_out, const void* a, const float* coef,
+                                int splits, void* da, int64_t N, int64_t P, int64_t Cp, x3d_dtype_t dt,
+                                x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0, "Cp % 8");
+  if (N * P == 0) return 0;
+  X3D_DISPATCH_DTYPE(dt, {
+    RowGeom g = make_row_geom<T>(N, P, Cp, 8 * kNumSMs);
+    dim3 grid(g.chunks, (unsigned)N);
+    if (mask_out)
+      bn_bwd_apply_kernel<T, true><<<grid, g.threads, 0, as_stream(stream)>>>(
+          (const T*)dout, (const T*)mask_out, (const T*)a, coef, splits, (T*)da, P, (int)Cp, g.cv, g.rows, g.chunk);
+    else
+      bn_bwd_apply_kernel<T, false><<<grid, g.threads, 0, as_stream(stream)>>>(
+          (const T*)dout, nullptr, (const T*)a, coef, splits, (T*)da, P, (int)Cp, g.cv, g.rows, g.chunk);
+  });
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+__global__ void relu_bwd_add_kernel(const T* __restrict__ dout, const T* __restrict__ out, T* __restrict__ dx,
+                                    int64_t nvec) {
+  constexpr int VEC = Vec<T>::N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float d[VEC], o[VEC], x[VEC];
+    load_vec<T>(dout + i * VEC, d);
+    load_vec<T>(out + i * VEC, o);
+    load_vec<T>(dx + i * VEC, x);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) x[j] += (o[j] > 0.f) ? d[j] : 0.f;
+    store_vec<T>(dx + i * VEC, x);
+  }
+}
+extern "C" int x3d_relu_bwd_add(const void* dout, const void* out, void* dx, int64_t numel, x3d_dtype_t dt,
+                                x3d_stream_t stream) {
+  X3D_CHECK_ARG(numel % 8 == 0, "numel % 8");
+  if (numel == 0) return 0;
+  X3D_DISPATCH_DTYPE(dt, {
+    int64_t nvec = numel / Vec<T>::N;
+    int64_t blocks = cdiv(nvec, 256);
+    if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+    relu_bwd_add_kernel<T><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)out, (T*)dx, nvec);
+  });
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// =======================================================================================
+// SE forward (tiny): one block per sample
+// =======================================================================================
+__global__ void se_fwd_kernel(const double* __restrict__ stats, const float* __restrict__ scale,
+                              const float* __restrict__ shift, int splits, double invP, int C, int Cp, int sw,
+                              const float* __restrict__ W1, const float* __restrict__ b1,
+                              const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ pooled,
+                              float* __restrict__ hidden, float* __restrict__ gate) {
+  extern __shared__ float sm[];
+  float* s_p = sm;        // [C]
+  float* s_h = sm + C;    // [sw]
+  const int n = blockIdx.x, b = n % splits;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mu = (float)(stats[((int64_t)n * Cp + c) * 2] * invP);
+    float p = fmaf(scale[b * Cp + c], mu, shift[b * Cp + c]);
+    s_p[c] = p;
+    pooled[(int64_t)n * C + c] = p;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  for (int j = warp; j < sw; j += nw) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(W1[(int64_t)j * C + c], s_p[c], acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float h = fmaxf(acc + b1[j], 0.f);
+      s_h[j] = h;
+      hidden[(int64_t)n * sw + j] = h;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+    float g = 0.f;
+    if (c < C) {
+      float acc = b2[c];
+      for (int j = 0; j < sw; ++j) acc = fmaf(W2[(int64_t)c * sw + j], s_h[j], acc);
+      g = 1.f / (1.f + expf(-acc));
+    }
+    gate[(int64_t)n * Cp + c] = g;
+  }
+}
+extern "C" int x3d_se_fwd(const double* stats, const float* scale, const float* shift, int splits, int64_t N,
+                          int64_t P, int64_t C, int64_t Cp, int sw, const float* W1, const float* b1,
+                          const float* W2, const float* b2, float* pooled, float* hidden, float* gate,
+                          x3d_stream_t stream) {
+  if (N == 0) return 0;
+  size_t smem = (C + sw) * sizeof(float);
+  se_fwd_kernel<<<(unsigned)N, 256, smem, as_stream(stream)>>>(stats, scale, shift, splits, 1.0 / (double)P, (int)C,
+                                                              (int)Cp, sw, W1, b1, W2, b2, pooled, hidden, gate);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// =======================================================================================
+// Swish (+ SE gate) forward / backward
+// =======================================================================================
+template <typename T, bool GATE>
+__global__ void swish_gate_fwd_kernel(const T* __restrict__ a2, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, int splits, const float* __restrict__ gate,
+                                      T* __restrict__ v, int64_t P, int Cp, int cv, int rows, int64_t chunk) {
+  ROW_PROLOGUE();
+  const int b = n % splits;
+  float sc[VEC], sh[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    float g = GATE ? gate[(int64_t)n * Cp + c0 + j] : 1.f;
+    sc[j] = scale[b * Cp + c0 + j] * g;   // z = g*(sc*a+sh)
+    sh[j] = shift[b * Cp + c0 + j] * g;
+  }
+  for (int64_t p = p0 + prow; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float x[VEC];
+    load_vec<T>(a2 + off, x);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float z = fmaf(x[j], sc[j], sh[j]);
+      x[j] = z * sigmoidf_(z);
+    }
+    store_vec<T>(v + off, x);
+  }
+}
+extern "C" int x3d_swish_gate_fwd(const void* a2, const float* scale, const float* shift, int splits,
+                                  const float* gate, void* v, int64_t N, int64_t P, int64_t Cp, x3d_dtype_t dt,
+                                  x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0, "Cp % 8");
+  if (N * P == 0) return 0;
+  X3D_DISPATCH_DTYPE(dt, {
+    RowGeom g = make_row_geom<T>(N, P, Cp, 8 * kNumSMs);
+    dim3 grid(g.chunks, (unsigned)N);
+    if (gate)
+      swish_gate_fwd_kernel<T, true><<<grid, g.threads, 0, as_stream(stream)>>>((const T*)a2, scale, shift, splits, gate,
+                                                                               (T*)v, P, (int)Cp, g.cv, g.rows, g.chunk);
+    else
+      swish_gate_fwd_kernel<T, false><<<grid, g.threads, 0, as_stream(stream)>>>((const T*)a2, scale, shift, splits,
+                                                                                nullptr, (T*)v, P, (int)Cp, g.cv, g.rows,
+                                                                                g.chunk);
+  });
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// d swish(z)/dz = s*(1 + z*(1-s)), s = sigmoid(z)   (x3d.py:81-84)
+__device__ __forceinline__ float swish_grad(float z) {
+  float s = sigmoidf_(z);
+  return s * fmaf(z, 1.f - s, 1.f);
+}
+
+template <typename T, bool GATE>
+__global__ void swish_gate_bwd_reduce_kernel(const T* __restrict__ dv, const T* __restrict__ a2,
+                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                             int splits, const float* __restrict__ gate, double* __restrict__ stats,
+                                             int64_t P, int Cp, int cv, int rows, int64_t chunk) {
+  extern __shared__ float s_acc[];
+  ROW_PROLOGUE();
+  const int b = n % splits;
+  float sc[VEC], sh[VEC], a0[VEC], a1[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    float g = GATE ? gate[(int64_t)n * Cp + c0 + j] : 1.f;
+    sc[j] = scale[b * Cp + c0 + j] * g;
+    sh[j] = shift[b * Cp + c0 + j] * g;
+    a0[j] = a1[j] = 0.f;
+  }
+  for (int64_t p = p0 + prow; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float d[VEC], x[VEC];
+    load_vec<T>(dv + off, d);
+    load_vec<T>(a2 + off, x);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float dz = d[j] * swish_grad(fmaf(x[j], sc[j], sh[j]));
+      a0[j] += dz;
+      a1[j] = fmaf(dz, x[j], a1[j]);
+    }
+  }
+  block_stats_flush<VEC>(a0, a1, cvec, Cp, s_acc, stats + (int64_t)n * Cp * 2);
+}
+extern "C" int x3d_swish_gate_bwd_reduce(const void* dv, const void* a2, const float* scale, const float* shift,
+                                         int splits, const float* gate, double* stats, int64_t N, int64_t P,
+                                         int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0, "Cp % 8");
+  if (N * P == 0) return 0;
+  X3D_DISPATCH_DTYPE(dt, {
+    RowGeom g = make_row_geom<T>(N, P, Cp);
+    dim3 grid(g.chunks, (unsigned)N);
+    size_t smem = Cp * 2 * sizeof(float);
+    if (gate)
+      swish_gate_bwd_reduce_kernel<T, true><<<grid, g.threads, smem, as_stream(stream)>>>(
+          (const T*)dv, (const T*)a2, scale, shift, splits, gate, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
+    else
+      swish_gate_bwd_reduce_kernel<T, false><<<grid, g.threads, smem, as_stream(stream)>>>(
+          (const T*)dv, (const T*)a2, scale, shift, splits, nullptr, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
+  });
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// SE backward for one sample (block per sample): produces work[n][c] = dp[n][c]/P and the SE
+// parameter gradients.  u = scale*a2+shift (bn2 output), z = gate*u, dz = dv*swish'(z).
+__global__ void se_bwd_sample_kernel(const double* __restrict__ fwd_stats, const double* __restrict__ bwd_stats,
+                                     int splits, double P, int C, int Cp, int sw, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, const float* __restrict__ W1,
+                                     const float* __restrict__ W2, const float* __restrict__ pooled,
+                                     const float* __restrict__ hidden, const float* __restrict__ gate,
+                                     float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
+                                     float* __restrict__ db2, float* __restrict__ work) {
+  extern __shared__ float sm[];
+  float* s_dz2 = sm;           // [C]
+  float* s_dz1 = sm + C;       // [sw]
+  float* s_h = sm + C + sw;    // [sw]
+  const int n = blockIdx.x, b = n % splits;
+  for (int j = threadIdx.x; j < sw; j += blockDim.x) s_h[j] = hidden[(int64_t)n * sw + j];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double R1 = bwd_stats[((int64_t)n * Cp + c) * 2 + 0];
+    const double R2 = bwd_stats[((int64_t)n * Cp + c) * 2 + 1];
+    const float g = gate[(int64_t)n * Cp + c];
+    // dgate = sum_thw dz*u = scale*sum(dz*a2) + shift*sum(dz)
+    const float dgate = (float)((double)scale[b * Cp + c] * R2 + (double)shift[b * Cp + c] * R1);
+    s_dz2[c] = dgate * g * (1.f - g);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  for (int j = warp; j < sw; j += nw) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(W2[(int64_t)c * sw + j], s_dz2[c], acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float dz1 = s_h[j] > 0.f ? acc : 0.f;
+      s_dz1[j] = dz1;
+      atomicAdd(&db1[j], dz1);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+    float dpP = 0.f;
+    if (c < C) {
+      float dp = 0.f;
+      const float dz2 = s_dz2[c];
+      const float pc = pooled[(int64_t)n * C + c];
+      for (int j = 0; j < sw; ++j) {
+        dp = fmaf(W1[(int64_t)j * C + c], s_dz1[j], dp);
+        atomicAdd(&dW2[(int64_t)c * sw + j], dz2 * s_h[j]);
+        atomicAdd(&dW1[(int64_t)j * C + c], s_dz1[j] * pc);
+      }
+      atomicAdd(&db2[c], dz2);
+      dpP = (float)((double)dp / P);
+    }
+    work[(int64_t)n * Cp + c] = dpP;
+  }
+}
+
+// BN2 backward coefficients per (n, c): da2 = E1*dz + E2*a2 + E3, with du = dz*g + dpP.
+__global__ void se_bn_bwd_coef_kernel(const double* __restrict__ fwd_stats, const double* __restrict__ bwd_stats,
+                                      int N, int splits, double P, int C, int Cp, const float* __restrict__ gamma,
+                                      const float* __restrict__ mean, const float* __restrict__ rstd, int train,
+                                      const float* __restrict__ gate /*nullable*/, const float* __restrict__ work,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                      float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  if (c >= C) {
+    for (int n = 0; n < N; ++n) {
+      float* e = coef + ((int64_t)n * Cp + c) * 3;
+      e[0] = e[1] = e[2] = 0.f;
+    }
+    return;
+  }
+  const double gm = gamma[c];
+  const double m = (double)(N / splits) * P;
+  double dgam = 0.0, dbet = 0.0;
+  for (int b = 0; b < splits; ++b) {
+    double s1 = 0.0, s2 = 0.0;   // sum du, sum du*a2 over the split
+    for (int n = b; n < N; n += splits) {
+      const double g = gate ? (double)gate[(int64_t)n * Cp + c] : 1.0;
+      const double dpP = gate ? (double)work[(int64_t)n * Cp + c] : 0.0;
+      s1 += g * bwd_stats[((int64_t)n * Cp + c) * 2 + 0] + dpP * P;
+      s2 += g * bwd_stats[((int64_t)n * Cp + c) * 2 + 1] + dpP * fwd_stats[((int64_t)n * Cp + c) * 2 + 0];
+    }
+    const double mu = mean[b * Cp + c], r = rstd[b * Cp + c];
+    const double sxh = (s2 - mu * s1) * r;
+    dgam += sxh;
+    dbet += s1;
+    double A = gm * r, B = 0.0, Cc = 0.0;
+    if (train) {
+      const double m1 = s1 / m, m2 = sxh / m;
+      B = -gm * r * r * m2;
+      Cc = gm * r * (-m1 + mu * r * m2);
+    }
+    for (int n = b; n < N; n += splits) {
+      const double g = gate ? (double)gate[(int64_t)n * Cp + c] : 1.0;
+      const double dpP = gate ? (double)work[(int64_t)n * Cp + c] : 0.0;
+      float* e = coef + ((int64_t)n * Cp + c) * 3;
+      e[0] = (float)(A * g);
+      e[1] = (float)B;
+      e[2] = (float)(Cc + A * dpP);
+    }
+  }
+  if (dgamma) dgamma[c] += (float)dgam;
+  if (dbeta) dbeta[c] += (float)dbet;
+}
+
+extern "C" int x3d_se_bn_bwd(const double* fwd_stats, const double* bwd_stats, int64_t N, int splits, int64_t P,
+                             int64_t C, int64_t Cp, int sw, const float* gamma, const float* mean,
+                             const float* rstd, const float* scale, const float* shift, int train,
+                             const float* W1, const float* W2, const float* pooled, const float* hidden,
+                             const float* gate, float* dW1, float* db1, float* dW2, float* db2, float* dgamma,
+                             float* dbeta, float* work, float* coef, x3d_stream_t stream) {
+  if (N == 0) return 0;
+  if (gate) {
+    size_t smem = (C + 2 * sw) * sizeof(float);
+    se_bwd_sample_kernel<<<(unsigned)N, 256, smem, as_stream(stream)>>>(fwd_stats, bwd_stats, splits, (double)P, (int)C,
+                                                                       (int)Cp, sw, scale, shift, W1, W2, pooled, hidden,
+                                                                       gate, dW1, db1, dW2, db2, work);
+    X3D_LAUNCH_CHECK();
+  }
+  se_bn_bwd_coef_kernel<<<(unsigned)cdiv(Cp, 64), 64, 0, as_stream(stream)>>>(fwd_stats, bwd_stats, (int)N, splits,
+                                                                           (double)P, (int)C, (int)Cp, gamma, mean, rstd,
+                                                                           train, gate, work, dgamma, dbeta, coef);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, bool GATE>
+__global__ void swish_gate_bwd_apply_kernel(const T* __restrict__ dv, const T* __restrict__ a2,
+                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                            int splits, const float* __restrict__ gate, const float* __restrict__ coef,
+                                            T* __restrict__ da2, int64_t P, int Cp, int cv, int rows, int64_t chunk) {
+  ROW_PROLOGUE();
+  const int b = n % splits;
+  float sc[VEC], sh[VEC], E1[VEC], E2[VEC], E3[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    float g = GATE ? gate[(int64_t)n * Cp + c0 + j] : 1.f;
+    sc[j] = scale[b * Cp + c0 + j] * g;
+    sh[j] = shift[b * Cp + c0 + j] * g;
+    const float* e = coef + ((int64_t)n * Cp + c0 + j) * 3;
+    E1[j] = e[0]; E2[j] = e[1]; E3[j] = e[2];
+  }
+  for (int64_t p = p0 + prow; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float d[VEC], x[VEC];
+    load_vec<T>(dv + off, d);
+    load_vec<T>(a2 + off, x);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float dz = d[j] * swish_grad(fmaf(x[j], sc[j], sh[j]));
+      d[j] = fmaf(E1[j], dz, fmaf(E2[j], x[j], E3[j]));
+    }
+    store_vec<T>(da2 + off, d);
+  }
+}
+extern "C" int x3d_swish_gate_bwd_apply(const void* dv, const void* a2, const float* scale, const float* shift,
+                                        int splits, const float* gate, const float* coef, void* da2, int64_t N,
+                                        int64_t P, int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0, "Cp % 8");
+  if (N * P == 0) return 0;
+  X3D_DISPATCH_DTYPE(dt, {
+    RowGeom g = make_row_geom<T>(N, P, Cp, 8 * kNumSMs);
+    dim3 grid(g.chunks, (unsigned)N);
+    if (gate)
+      swish_gate_bwd_apply_kernel<T, true><<<grid, g.threads, 0, as_stream(stream)>>>(
+          (const T*)dv, (const T*)a2, scale, shift, splits, gate, coef, (T*)da2, P, (int)Cp, g.cv, g.rows, g.chunk);
+    else
+      swish_gate_bwd_apply_kernel<T, false><<<grid, g.threads, 0, as_stream(stream)>>>(
+          (const T*)dv, (const T*)a2, scale, shift, splits, nullptr, coef, (T*)da2, P, (int)Cp, g.cv, g.rows, g.chunk);
+  });
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// =======================================================================================
+// head: relu(bn5) -> average pool ; backward into BN
+// rows r = n (pool_t) or n*T+t; Pp positions per row.
+// =======================================================================================
+template <typename T>
+__global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ a, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, int splits, float* __restrict__ pooled,
+                                        int rows_per_sample, int64_t P /*positions per row*/, int C, int Cp, int cv,
+                                        int rows, int64_t chunk) {
+  extern __shared__ float s_acc[];
+  ROW_PROLOGUE();   // here "n" is the pooled row r
+  const int b = (n / rows_per_sample) % splits;
+  float sc[VEC], sh[VEC], a0[VEC], a1[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    sc[j] = scale[b * Cp + c0 + j];
+    sh[j] = shift[b * Cp + c0 + j];
+    a0[j] = 0.f; a1[j] = 0.f;
+  }
+  for (int64_t p = p0 + prow; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float x[VEC];
+    load_vec<T>(a + off, x);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) a0[j] += fmaxf(fmaf(x[j], sc[j], sh[j]), 0.f);
+  }
+  for (int i = threadIdx.x; i < Cp; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) atomicAdd(&s_acc[c0 + j], a0[j]);
+  __syncthreads();
+  const float inv = 1.f / (float)P;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&pooled[(int64_t)n * C + i], s_acc[i] * inv);
+  (void)a1;
+}
+extern "C" int x3d_bn_relu_pool_fwd(const void* a5, const float* scale, const float* shift, int splits,
+                                    float* pooled, int64_t N, int64_t T_, int64_t HW, int pool_t, int64_t C,
+                                    int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0, "Cp % 8");
+  const int64_t R = pool_t ? N : N * T_;
+  const int64_t Pp = pool_t ? T_ * HW : HW;
+  if (R * Pp == 0) return 0;
+  cudaError_t e = cudaMemsetAsync(pooled, 0, sizeof(float) * R * C, as_stream(stream));
+  if (e != cudaSuccess) { set_error("memset failed"); return (int)e; }
+  X3D_DISPATCH_DTYPE(dt, {
+    RowGeom g = make_row_geom<T>(R, Pp, Cp);
+    dim3 grid(g.chunks, (unsigned)R);
+    bn_relu_pool_fwd_kernel<T><<<grid, g.threads, Cp * sizeof(float), as_stream(stream)>>>(
+        (const T*)a5, scale, shift, splits, pooled, pool_t ? 1 : (int)T_, Pp, (int)C, (int)Cp, g.cv, g.rows, g.chunk);
+  });
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, bool APPLY>
+__global__ void bn_relu_pool_bwd_kernel(const T* __restrict__ a, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, int splits,
+                                        const float* __restrict__ dpooled, double* __restrict__ stats,
+                                        const float* __restrict__ coef, T* __restrict__ da, int rows_per_sample,
+                                        int64_t P, int C, int Cp, int cv, int rows, int64_t chunk) {
+  extern __shared__ float s_acc[];
+  ROW_PROLOGUE();   // n = pooled row r
+  const int ns = n / rows_per_sample;   // sample index
+  const int b = ns % splits;
+  const int sC = splits * Cp;
+  float sc[VEC], sh[VEC], dpl[VEC], a0[VEC], a1[VEC], A[VEC], B[VEC], Cc[VEC];
+  const float inv = 1.f / (float)P;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    sc[j] = scale[b * Cp + c0 + j];
+    sh[j] = shift[b * Cp + c0 + j];
+    dpl[j] = (c0 + j < C) ? dpooled[(int64_t)n * C + c0 + j] * inv : 0.f;
+    a0[j] = a1[j] = 0.f;
+    if (APPLY) {
+      A[j] = coef[0 * sC + b * Cp + c0 + j];
+      B[j] = coef[1 * sC + b * Cp + c0 + j];
+      Cc[j] = coef[2 * sC + b * Cp + c0 + j];
+    }
+  }
+  for (int64_t p = p0 + prow; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float x[VEC];
+    load_vec<T>(a + off, x);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float dp = (fmaf(x[j], sc[j], sh[j]) > 0.f) ? dpl[j] : 0.f;
+      if (APPLY) {
+        x[j] = fmaf(A[j], dp, fmaf(B[j], x[j], Cc[j]));
+      } else {
+        a0[j] += dp;
+        a1[j] = fmaf(dp, x[j], a1[j]);
+      }
+    }
+    if (APPLY) store_vec<T>(da + off, x);
+  }
+  if (!APPLY) block_stats_flush<VEC>(a0, a1, cvec, Cp, s_acc, stats + (int64_t)ns * Cp * 2);
+}
+extern "C" int x3d_bn_relu_pool_bwd_reduce(const void* a5, const float* scale, const float* shift, int splits,
+                                           const float* dpooled, double* stats, int64_t N, int64_t T_, int64_t HW,
+                                           int pool_t, int64_t C, int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0, "Cp % 8");
+  const int64_t R = pool_t ? N : N * T_;
+  const int64_t Pp = pool_t ? T_ * HW : HW;
+  if (R * Pp == 0) return 0;
+  X3D_DISPATCH_DTYPE(dt, {
+    RowGeom g = make_row_geom<T>(R, Pp, Cp);
+    dim3 grid(g.chunks, (unsigned)R);
+    bn_relu_pool_bwd_kernel<T, false><<<grid, g.threads, Cp * 2 * sizeof(float), as_stream(stream)>>>(
+        (const T*)a5, scale, shift, splits, dpooled, stats, nullptr, nullptr, pool_t ? 1 : (int)T_, Pp, (int)C, (int)Cp,
+        g.cv, g.rows, g.chunk);
+  });
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int x3d_bn_relu_pool_bwd_apply(const void* a5, const float* scale, const float* shift, int splits,
+                                          const float* dpooled, const float* coef, void* da5, int64_t N, int64_t T_,
+                                          int64_t HW, int pool_t, int64_t C, int64_t Cp, x3d_dtype_t dt,
+                                          x3d_stream_t stream) {
+  X3D_CHECK_ARG(Cp % 8 == 0, "Cp % 8");
+  const int64_t R = pool_t ? N : N * T_;
+  const int64_t Pp = pool_t ? T_ * HW : HW;
+  if (R * Pp == 0) return 0;
+  X3D_DISPATCH_DTYPE(dt, {
+    RowGeom g = make_row_geom<T>(R, Pp, Cp, 8 * kNumSMs);
+    dim3 grid(g.chunks, (unsigned)R);
+    bn_relu_pool_bwd_kernel<T, true><<<grid, g.threads, Cp * 2 * sizeof(float), as_stream(stream)>>>(
+        (const T*)a5, scale, shift, splits, dpooled, nullptr, coef, (T*)da5, pool_t ? 1 : (int)T_, Pp, (int)C, (int)Cp,
+        g.cv, g.rows, g.chunk);
+  });
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// =======================================================================================
+// small dense fp32 GEMM (head fc1/fc2 and their gradients): 32x32x32 smem tiles
+// =======================================================================================
+__global__ void small_gemm_kernel(const float* __restrict__ A, int64_t sai, int64_t sak, const float* __restrict__ B,
+                                  int64_t sbk, int64_t sbj, float* __restrict__ C, int64_t ldc, int M, int Nn, int K,
+                                  const float* __restrict__ bias, int relu, const float* __restrict__ mul,
+                                  int accumulate) {
+  __shared__ float As[32][33];  // [i][k]
+  __shared__ float Bs[32][33];  // [k][j]
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    // A tile: fastest thread index follows the unit-stride dimension
+    for (int r = ty; r < 32; r += 8) {
+      int i, k;
+      if (sak == 1) { i = r; k = tx; } else { i = tx; k = r; }
+      As[i][k] = (i0 + i < M && k0 + k < K) ? A[(int64_t)(i0 + i) * sai + (int64_t)(k0 + k) * sak] : 0.f;
+    }
+    for (int r = ty; r < 32; r += 8) {
+      int k, j;
+      if (sbj == 1) { k = r; j = tx; } else { k = tx; j = r; }
+      Bs[k][j] = (k0 + k < K && j0 + j < Nn) ? B[(int64_t)(k0 + k) * sbk + (int64_t)(j0 + j) * sbj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float bv = Bs[k][tx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(As[ty + 8 * q][k], bv, acc[q]);
+    }
+    __syncthreads();
+  }
+  const int j = j0 + tx;
+  if (j < Nn) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int i = i0 + ty + 8 * q;
+      if (i < M) {
+        float v = acc[q] + (bias ? bias[j] : 0.f);
+        if (relu) v = fmaxf(v, 0.f);
+        if (mul) v *= mul[(int64_t)i * Nn + j];
+        float* dst = &C[(int64_t)i * ldc + j];
+        *dst = accumulate ? (*dst + v) : v;
+      }
+    }
+  }
+}
+extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
+                              float* C, int64_t ldc, int64_t M, int64_t Nn, int64_t K, const float* bias, int relu,
+                              const float* mul, int accumulate, x3d_stream_t stream) {
+  if (M == 0 || Nn == 0) return 0;
+  dim3 grid((unsigned)cdiv(Nn, 32), (unsigned)cdiv(M, 32)), block(32, 8);
+  small_gemm_kernel<<<grid, block, 0, as_stream(stream)>>>(A, sai, sak, B, sbk, sbj, C, ldc, (int)M, (int)Nn, (int)K,
+                                                          bias, relu, mul, accumulate);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void colsum_kernel(const float* __restrict__ src, int M, int Nn, float* __restrict__ dst) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Nn) return;
+  float acc = 0.f;
+  for (int i = 0; i < M; ++i) acc += src[(int64_t)i * Nn + j];
+  dst[j] += acc;
+}
+extern "C" int x3d_colsum(const float* src, int64_t M, int64_t Nn, float* dst, x3d_stream_t stream) {
+  if (Nn == 0) return 0;
+  colsum_kernel<<<(unsigned)cdiv(Nn, 128), 128, 0, as_stream(stream)>>>(src, (int)M, (int)Nn, dst);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void relu_mask_mul_kernel(const float* __restrict__ src, const float* __restrict__ ref,
+                                     const float* __restrict__ mul, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = ref[i] > 0.f ? src[i] : 0.f;
+    if (mul) v *= mul[i];
+    dst[i] = v;
+  }
+}
+extern "C" int x3d_relu_mask_mul(const float* src, const float* ref, const float* mul, float* dst, int64_t numel,
+                                 x3d_stream_t stream) {
+  if (numel == 0) return 0;
+  int64_t blocks = cdiv(numel, 256);
+  if (blocks > 1024) blocks = 1024;
+  relu_mask_mul_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, ref, mul, dst, numel);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// =======================================================================================
+// fused SGD (momentum, weight decay; torch.optim.SGD semantics, dampening 0, no nesterov)
+// =======================================================================================
+__global__ void sgd_kernel(const x3d_sgd_desc_t* __restrict__ descs, float lr, float momentum, float wd,
+                           float grad_scale, int first_step) {
+  const x3d_sgd_desc_t d = descs[blockIdx.y];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.numel; i += (int64_t)gridDim.x * blockDim.x) {
+    float p = d.param[i];
+    float g = fmaf(wd, p, d.grad[i] * grad_scale);
+    if (momentum != 0.f) {
+      float buf = first_step ? g : fmaf(momentum, d.momentum_buf[i], g);
+      d.momentum_buf[i] = buf;
+      g = buf;
+    }
+    d.param[i] = fmaf(-lr, g, p);
+  }
+}
+extern "C" int x3d_sgd_step(const x3d_sgd_desc_t* descs_dev, int n_desc, int64_t max_numel, float lr,
+                            float momentum, float weight_decay, float grad_scale, int first_step,
+                            x3d_stream_t stream) {
+  if (n_desc == 0) return 0;
+  int64_t bx = cdiv(max_numel, 256 * 4);
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  sgd_kernel<<<dim3((unsigned)bx, (unsigned)n_desc), 256, 0, as_stream(stream)>>>(descs_dev, lr, momentum, weight_decay,
+                                                                              grad_scale, first_step);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,169 @@
+// Stem conv1_s: dense (1,3,3) conv, stride (1,2,2), pad (0,1,1), Ci (<=3) -> Co channels.
+// Reads the user-facing NCDHW fp32 clip directly, writes NDHWC.  Replaces the cuDNN kernel behind
+// nn.Conv3d at x3d.py:196-201 / :317.   TAPS = Ci*9 <= 27.
+#include "common.cuh"
+
+using namespace x3d;
+
+constexpr int STEM_MAX_TAPS = 27;
+
+template <typename T>
+__global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        T* __restrict__ y, int Ci, int T_, int H, int W, int Ho,
+                                                        int Wo, int Co, int Cop, int64_t total) {
+  extern __shared__ float s_w[];  // [taps][Cop]
+  const int taps = Ci * 9;
+  for (int i = threadIdx.x; i < taps * Cop; i += blockDim.x) {
+    const int tap = i / Cop, c = i % Cop;
+    s_w[i] = (c < Co) ? w[(int64_t)c * taps + tap] : 0.f;  // w[co][ci][0][j][k] -> tap = ci*9 + j*3 + k
+  }
+  __syncthreads();
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int wo = (int)(p % Wo);
+  int64_t r = p / Wo;
+  const int ho = (int)(r % Ho);
+  r /= Ho;
+  const int t = (int)(r % T_);
+  const int n = (int)(r / T_);
+  float xin[STEM_MAX_TAPS];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int hh = 2 * ho + j - 1, ww = 2 * wo + k - 1;
+        float v = 0.f;
+        if (ci < Ci && hh >= 0 && hh < H && ww >= 0 && ww < W)
+          v = __ldg(&x[((((int64_t)n * Ci + ci) * T_ + t) * H + hh) * W + ww]);
+        xin[ci * 9 + j * 3 + k] = v;
+      }
+    }
+  }
+  T* yp = y + p * Cop;
+  for (int c8 = 0; c8 < Cop; c8 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < STEM_MAX_TAPS; ++tap) {
+      if (tap < taps) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tap * Cop + c8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tap * Cop + c8 + 4]);
+        const float xv = xin[tap];
+        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+        acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+        acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+      }
+    }
+    if (sizeof(T) == 2) {
+      uint4 q;
+      q.x = pack_bf16x2(acc[0], acc[1]); q.y = pack_bf16x2(acc[2], acc[3]);
+      q.z = pack_bf16x2(acc[4], acc[5]); q.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(yp + c8) = q;
+    } else {
+      float* yf = reinterpret_cast<float*>(yp) + c8;
+      *reinterpret_cast<float4*>(yf) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(yf + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
+extern "C" int x3d_stem_conv_s_fwd(const float* x, const float* w, void* y, int64_t N, int64_t Ci, int64_t T_,
+                                   int64_t H, int64_t W, int64_t Co, int64_t Cop, x3d_dtype_t dt,
+                                   x3d_stream_t stream) {
+  X3D_CHECK_ARG(Ci >= 1 && Ci <= 3, "n_input_channels must be <= 3");
+  X3D_CHECK_ARG(Cop % 8 == 0 && Cop >= Co, "Cop");
+  const int Ho = (int)((H + 2 - 3) / 2 + 1), Wo = (int)((W + 2 - 3) / 2 + 1);
+  const int64_t total = N * T_ * Ho * Wo;
+  if (total == 0) return 0;
+  size_t smem = (size_t)Ci * 9 * Cop * sizeof(float);
+  X3D_DISPATCH_DTYPE(dt, (stem_fwd_kernel<T><<<(unsigned)cdiv(total, 128), 128, smem, as_stream(stream)>>>(
+                             x, w, (T*)y, (int)Ci, (int)T_, (int)H, (int)W, Ho, Wo, (int)Co, (int)Cop, total)));
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+
+// wgrad: dw[co][tap] += sum_p dy[p][co] * xcol[p][tap].  Block: 256 threads = 32 taps x 8 channel groups.
+constexpr int SW_POS = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                                          float* __restrict__ dw, int Ci, int T_, int H, int W,
+                                                          int Ho, int Wo, int Co, int Cop, int64_t total,
+                                                          int64_t pos_per_block) {
+  extern __shared__ float sm[];
+  float* Xs = sm;                   // [SW_POS][32]
+  float* Ds = sm + SW_POS * 32;     // [SW_POS][Cop]
+  const int taps = Ci * 9;
+  const int tap = threadIdx.x / 8, cg = threadIdx.x % 8;
+  const int cpt = Cop / 8;          // channels per thread (3 or 4 ...)
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const int64_t pb = (int64_t)blockIdx.x * pos_per_block;
+  const int64_t pe = (pb + pos_per_block < total) ? pb + pos_per_block : total;
+  for (int64_t ps = pb; ps < pe; ps += SW_POS) {
+    // im2col tile
+    for (int i = threadIdx.x; i < SW_POS * 32; i += 256) {
+      const int pp = i / 32, tp = i % 32;
+      const int64_t p = ps + pp;
+      float v = 0.f;
+      if (p < pe && tp < taps) {
+        const int wo = (int)(p % Wo);
+        int64_t r = p / Wo;
+        const int ho = (int)(r % Ho);
+        r /= Ho;
+        const int t = (int)(r % T_);
+        const int n = (int)(r / T_);
+        const int ci = tp / 9, j = (tp % 9) / 3, k = tp % 3;
+        const int hh = 2 * ho + j - 1, ww = 2 * wo + k - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(&x[((((int64_t)n * Ci + ci) * T_ + t) * H + hh) * W + ww]);
+      }
+      Xs[i] = v;
+    }
+    for (int i = threadIdx.x; i < SW_POS * Cop; i += 256) {
+      const int pp = i / Cop;
+      const int64_t p = ps + pp;
+      Ds[i] = (p < pe) ? to_float<T>(dy[p * Cop + (i % Cop)]) : 0.f;
+    }
+    __syncthreads();
+    if (tap < taps) {
+#pragma unroll 4
+      for (int pp = 0; pp < SW_POS; ++pp) {
+        const float xv = Xs[pp * 32 + tap];
+        const float* dp = &Ds[pp * Cop + cg * cpt];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < cpt) acc[j] = fmaf(xv, dp[j], acc[j]);
+      }
+    }
+    __syncthreads();
+  }
+  if (tap < taps) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * cpt + j;
+      if (j < cpt && c < Co && acc[j] != 0.f) atomicAdd(&dw[(int64_t)c * taps + tap], acc[j]);
+    }
+  }
+}
+
+extern "C" int x3d_stem_conv_s_wgrad(const float* x, const void* dy, float* dw, int64_t N, int64_t Ci, int64_t T_,
+                                     int64_t H, int64_t W, int64_t Co, int64_t Cop, x3d_dtype_t dt,
+                                     x3d_stream_t stream) {
+  X3D_CHECK_ARG(Ci >= 1 && Ci <= 3, "n_input_channels must be <= 3");
+  X3D_CHECK_ARG(Cop % 8 == 0 && Cop >= Co && Cop <= 64, "Cop must be a multiple of 8, <= 64");
+  const int Ho = (int)((H + 2 - 3) / 2 + 1), Wo = (int)((W + 2 - 3) / 2 + 1);
+  const int64_t total = N * T_ * Ho * Wo;
+  if (total == 0) return 0;
+  int64_t blocks = 4 * kNumSMs;
+  int64_t ppb = cdiv(cdiv(total, blocks), SW_POS) * SW_POS;
+  blocks = cdiv(total, ppb);
+  size_t smem = (size_t)(SW_POS * 32 + SW_POS * Cop) * sizeof(float);
+  X3D_DISPATCH_DTYPE(dt, (stem_wgrad_kernel<T><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
+                             x, (const T*)dy, dw, (int)Ci, (int)T_, (int)H, (int)W, Ho, Wo, (int)Co, (int)Cop, total, ppb)));
+  X3D_LAUNCH_CHECK();
+  return 0;
+}

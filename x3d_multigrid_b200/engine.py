@@ -1,0 +1,575 @@
+"""Host-side orchestration of the X3D forward / backward over the C ABI (libx3d_b200.so).
+
+PyTorch is used here for device memory (torch.empty), streams and nothing else: every
+arithmetic step of the network is a kernel of the shared library.  Dataflow per Bottleneck
+(x3d.py:143-171), NDHWC, "raw" = conv output before its SubBatchNorm3d:
+
+  x --pw GEMM(+stats)--> a1 --[bn1+relu fused on load] dw 3x3x3 (+stats,+SE sums)--> a2
+    --bn2 finalize, SE fc--> swish(gate*bn2(a2)) = v --pw GEMM(+stats)--> a3
+    --relu(bn3(a3) + residual)--> out
+
+Backward mirrors it with two-pass BN backward (reduce -> tiny finalize -> apply); all
+parameter gradients are accumulated by the kernels into one flat fp32 buffer laid out in
+reverse-stage bucket order (so a data-parallel allreduce can start while earlier stages
+are still running backward).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, PackDesc
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class BNState:
+    scale: torch.Tensor    # [s][Cp] fp32
+    shift: torch.Tensor
+    mean: torch.Tensor
+    rstd: torch.Tensor
+    splits: int
+    train: bool
+
+
+class Arena:
+    """Zero-initialised bump allocator for the small per-step statistic buffers.
+
+    First use of a given step signature measures the need with individual torch.zeros;
+    later steps carve one buffer that is cleared with a single memset."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf: Optional[torch.Tensor] = None
+        self.off = 0
+        self.need = 0
+        self.keep: List[torch.Tensor] = []
+
+    def begin(self):
+        if self.need > 0 and (self.buf is None or self.buf.numel() < self.need):
+            self.buf = torch.empty(self.need, dtype=torch.uint8, device=self.device)
+        if self.buf is not None:
+            self.buf.zero_()
+        self.off = 0
+        self.keep = []
+
+    def zeros(self, nbytes: int) -> torch.Tensor:
+        nbytes = (nbytes + 255) // 256 * 256
+        if self.buf is not None and self.off + nbytes <= self.buf.numel():
+            t = self.buf[self.off:self.off + nbytes]
+            self.off += nbytes
+        else:
+            t = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            self.keep.append(t)
+            self.off += nbytes
+        self.need = max(self.need, self.off)
+        return t
+
+
+class _ParamRef:
+    """One nn.Parameter of the model plus its slot in the flat gradient buffer."""
+    __slots__ = ('name', 'param', 'goff', 'numel')
+
+    def __init__(self, name, param, goff):
+        self.name, self.param, self.goff, self.numel = name, param, goff, param.numel()
+
+
+class Engine:
+    """Runs ResNet.forward / backward of ``model`` (x3d_multigrid_b200.x3d.ResNet) on CUDA."""
+
+    def __init__(self, model, dtype: torch.dtype):
+        assert dtype in (torch.float32, torch.bfloat16)
+        self.model = model
+        self.dtype = dtype
+        self.dt = BF16 if dtype == torch.bfloat16 else F32
+        self.lib = _lib.lib()
+        self.device = None
+        self._sig = None
+        self.arena_f: Optional[Arena] = None
+        self.arena_b: Optional[Arena] = None
+        self.grad_hook: Optional[Callable[[int], None]] = None   # called after each bucket's grads are final
+
+    # ------------------------------------------------------------------ parameter tables
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _signature(self):
+        return tuple((p.data_ptr(), tuple(p.shape)) for p in self.model.parameters())
+
+    def prepare(self, device):
+        """(Re)build the parameter tables when parameters moved / were replaced."""
+        sig = self._signature()
+        if self._sig == sig and self.device == device:
+            return
+        self._sig = sig
+        self.device = device
+        m = self.model
+        for p in m.parameters():
+            if p.device != device or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError('all parameters must be contiguous fp32 tensors on the input device')
+        self.arena_f, self.arena_b = Arena(device), Arena(device)
+
+        # ---- flat gradient buffer, bucket order: head+stage4 first ... stem last
+        named = dict(m.named_parameters())
+        self.is_net = hasattr(m, 'conv1_s')
+        if self.is_net:
+            head = [k for k in named if k.split('.')[0] in ('conv5', 'bn5', 'fc1', 'fc2')]
+            buckets = [head + [k for k in named if k.startswith('layer4.')],
+                       [k for k in named if k.startswith('layer3.')],
+                       [k for k in named if k.startswith('layer2.')],
+                       [k for k in named if k.startswith('layer1.')] +
+                       [k for k in named if k.split('.')[0] in ('conv1_s', 'conv1_t', 'bn1')]]
+        else:
+            buckets = [list(named)]
+        self.refs: Dict[str, _ParamRef] = {}
+        off = 0
+        self.bucket_ranges: List[Tuple[int, int]] = []
+        for b in buckets:
+            start = off
+            for k in b:
+                self.refs[k] = _ParamRef(k, named[k], off)
+                off += (named[k].numel() + 3) // 4 * 4
+            self.bucket_ranges.append((start, off))
+        assert len(self.refs) == len(named), 'unassigned parameters'
+        self.gflat_numel = off
+        self.gflat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.param_order = [self.refs[k] for k in named]          # named_parameters() order
+
+        # ---- packed operand buffers
+        esz = 2 if self.dt == BF16 else 4
+        descs: List[PackDesc] = []
+        plan: List[Tuple[str, str, int, int, int, int, int, int, int]] = []
+        cur = 0
+
+        def reserve(nbytes):
+            nonlocal cur
+            o = cur
+            cur += (nbytes + 255) // 256 * 256
+            return o
+
+        self.packed: Dict[str, Tuple[int, int, int]] = {}   # key -> (byte offset, rows, cols)
+
+        def add_pw(name):     # [N][K][1,1,1] -> Wf [Np][Kp] and Wt [Kp][Np] in activation dtype
+            w = named[name + '.weight']
+            n, k = w.shape[0], w.shape[1]
+            np_, kp = pad8(n), pad8(k)
+            of = reserve(np_ * kp * esz)
+            ot = reserve(np_ * kp * esz)
+            plan.append((name + '.weight', 'f', of, n, k, np_, kp, 0, self.dt))
+            plan.append((name + '.weight', 't', ot, n, k, kp, np_, 1, self.dt))
+            self.packed[name + '.f'] = (of, np_, kp)
+            self.packed[name + '.t'] = (ot, kp, np_)
+
+        def add_dw(name):     # [C][1][kt][kh][kw] -> [taps][Cp] fp32
+            w = named[name + '.weight']
+            c, taps = w.shape[0], w.shape[2] * w.shape[3] * w.shape[4]
+            cp = pad8(c)
+            o = reserve(taps * cp * 4)
+            plan.append((name + '.weight', 'd', o, c, taps, taps, cp, 1, F32))
+            self.packed[name + '.d'] = (o, taps, cp)
+
+        if self.is_net:
+            add_dw('conv1_t')
+        for blk in m.blocks():
+            add_pw(blk.prefix + '.conv1')
+            add_dw(blk.prefix + '.conv2')
+            add_pw(blk.prefix + '.conv3')
+            if blk.downsample is not None:
+                add_pw(blk.prefix + '.downsample.0')
+        if self.is_net:
+            add_pw('conv5')
+        self.pack_buf = torch.zeros(max(cur, 256), dtype=torch.uint8, device=device)
+        base = self.pack_buf.data_ptr()
+        arr = (PackDesc * len(plan))()
+        max_elems = 1
+        for i, (pname, _kind, o, rows, cols, drows, dcols, tr, dtp) in enumerate(plan):
+            arr[i] = PackDesc(named[pname].data_ptr(), base + o, rows, cols, drows, dcols, tr, dtp)
+            max_elems = max(max_elems, drows * dcols)
+        raw = bytes(arr)
+        self.pack_descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        self.n_pack = len(plan)
+        self.pack_max = max_elems
+
+    def pk(self, key):
+        return self.pack_buf.data_ptr() + self.packed[key][0]
+
+    def g(self, name):
+        """device pointer of the gradient slot of parameter ``name``"""
+        r = self.refs[name]
+        return self.gflat.data_ptr() + 4 * r.goff
+
+    def p(self, name):
+        return self.refs[name].param.data_ptr()
+
+    def new_grad_buffer(self):
+        """fresh zeroed flat gradient buffer (the previous one may be owned by .grad views)"""
+        self.gflat = torch.zeros(self.gflat_numel, dtype=torch.float32, device=self.device)
+
+    def param_grads(self):
+        return [self.gflat[r.goff:r.goff + r.numel].view(r.param.shape) for r in self.param_order]
+
+    def to_ndhwc(self, x: torch.Tensor) -> torch.Tensor:
+        """NCDHW fp32 -> internal NDHWC (activation dtype, channels padded to 8)"""
+        N, C, T, H, W = x.shape
+        out = self._act(N, T, H, W, pad8(C))
+        self.lib.call('x3d_ncdhw_to_ndhwc', _ptr(x), _ptr(out), N, C, pad8(C), T, H, W, self.dt, self._stream())
+        return out
+
+    def to_ncdhw(self, x: torch.Tensor, C: int) -> torch.Tensor:
+        N, T, H, W, Cp = x.shape
+        out = self._f32(N, C, T, H, W)
+        self.lib.call('x3d_ndhwc_to_ncdhw', _ptr(x), _ptr(out), N, C, Cp, T, H, W, self.dt, self._stream())
+        return out
+
+    def pack_weights(self):
+        self.lib.call('x3d_pack_params', self.pack_descs.data_ptr(), self.n_pack, self.pack_max, self._stream())
+
+    # ------------------------------------------------------------------ small helpers
+    def _act(self, *shape):
+        return torch.empty(shape, dtype=self.dtype, device=self.device)
+
+    def _f32(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def _bn_forward_state(self, bn_mod, prefix, stats, N, P, C, Cp, training) -> BNState:
+        """SubBatchNorm3d statistics -> scale/shift (x3d.py:47-58)."""
+        lib, st = self.lib, self._stream()
+        if training:
+            s = int(bn_mod.num_splits)
+            if N % s != 0:
+                raise RuntimeError(f'batch {N} not divisible by num_splits {s} (x3d.py:50)')
+            buf = self._f32(4, s, Cp)
+            sb = bn_mod.split_bn
+            track = sb.track_running_stats and sb.running_mean is not None
+            lib.call('x3d_bn_finalize', _ptr(stats), N, s, P, C, Cp, self.p(prefix + '.weight'),
+                     self.p(prefix + '.bias'), _ptr(sb.running_mean) if track else None,
+                     _ptr(sb.running_var) if track else None,
+                     _ptr(sb.num_batches_tracked) if track else None,
+                     float(sb.momentum if sb.momentum is not None else BN_MOMENTUM), float(sb.eps),
+                     _ptr(buf[0]), _ptr(buf[1]), _ptr(buf[2]), _ptr(buf[3]), st)
+            return BNState(buf[0], buf[1], buf[2], buf[3], s, True)
+        buf = self._f32(4, 1, Cp)
+        bn = bn_mod.bn
+        lib.call('x3d_bn_eval_params', self.p(prefix + '.weight'), self.p(prefix + '.bias'),
+                 _ptr(bn.running_mean), _ptr(bn.running_var), C, Cp, float(bn.eps),
+                 _ptr(buf[0]), _ptr(buf[1]), _ptr(buf[2]), _ptr(buf[3]), st)
+        return BNState(buf[0], buf[1], buf[2], buf[3], 1, False)
+
+    def _stats(self, arena: Arena, N, Cp):
+        return arena.zeros(N * Cp * 2 * 8)
+
+    def _bn_backward(self, arena, prefix, bn: BNState, dout, mask_out, a, N, P, C, Cp, da):
+        """Two-pass BN backward: returns da (may alias dout)."""
+        lib, st = self.lib, self._stream()
+        bst = self._stats(arena, N, Cp)
+        lib.call('x3d_bn_bwd_reduce', _ptr(dout), _ptr(mask_out), _ptr(a), _ptr(bst), N, P, Cp, self.dt, st)
+        coef = self._f32(3, bn.splits, Cp)
+        lib.call('x3d_bn_bwd_finalize', _ptr(bst), N, bn.splits, P, C, Cp, self.p(prefix + '.weight'),
+                 _ptr(bn.mean), _ptr(bn.rstd), int(bn.train), _ptr(coef), self.g(prefix + '.weight'),
+                 self.g(prefix + '.bias'), st)
+        lib.call('x3d_bn_bwd_apply', _ptr(dout), _ptr(mask_out), _ptr(a), _ptr(coef), bn.splits, _ptr(da),
+                 N, P, Cp, self.dt, st)
+        return da
+
+    # ------------------------------------------------------------------ stem
+    def _stem_fwd(self, x, training, save):
+        m, lib, st = self.model, self.lib, self._stream()
+        N, Ci, T, H, W = x.shape
+        C0 = m.conv1_s.out_channels
+        C0p = pad8(C0)
+        H1, W1 = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        a_s = self._act(N, T, H1, W1, C0p)
+        lib.call('x3d_stem_conv_s_fwd', _ptr(x), self.p('conv1_s.weight'), _ptr(a_s), N, Ci, T, H, W, C0, C0p,
+                 self.dt, st)
+        a_t = self._act(N, T, H1, W1, C0p)
+        P = T * H1 * W1
+        st0 = self._stats(self.arena_f, N, C0p) if training else None
+        lib.call('x3d_dwconv_fwd', _ptr(a_s), self.pk('conv1_t.d'), _ptr(a_t), N, T, H1, W1, C0p, 5, 1, 1, 1,
+                 None, None, 1, 0, _ptr(st0), self.dt, st)
+        bn0 = self._bn_forward_state(m.bn1, 'bn1', st0, N, P, C0, C0p, training)
+        x0 = self._act(N, T, H1, W1, C0p)
+        lib.call('x3d_bn_act_fwd', _ptr(a_t), _ptr(bn0.scale), _ptr(bn0.shift), bn0.splits, None, None, None, 1,
+                 _ptr(x0), N, P, C0p, self.dt, st)
+        if save is not None:
+            save['stem'] = (x, a_s, a_t, bn0, x0)
+        return x0, (N, T, H1, W1)
+
+    def _stem_bwd(self, save, dx0):
+        m, lib, st = self.model, self.lib, self._stream()
+        x, a_s, a_t, bn0, x0 = save['stem']
+        N, Ci, T, H, W = x.shape
+        _, _, H1, W1, C0p = a_s.shape
+        C0 = m.conv1_s.out_channels
+        P = T * H1 * W1
+        da_t = self._bn_backward(self.arena_b, 'bn1', bn0, dx0, x0, a_t, N, P, C0, C0p, dx0)
+        lib.call('x3d_dwconv_wgrad', _ptr(a_s), _ptr(da_t), self.g('conv1_t.weight'), N, T, H1, W1, C0, C0p,
+                 5, 1, 1, 1, None, None, 1, 0, self.dt, st)
+        da_s = self._act(N, T, H1, W1, C0p)
+        lib.call('x3d_dwconv_dgrad', _ptr(da_t), self.pk('conv1_t.d'), _ptr(da_s), N, T, H1, W1, C0p, 5, 1, 1, 1,
+                 None, None, None, 1, None, self.dt, st)
+        lib.call('x3d_stem_conv_s_wgrad', _ptr(x), _ptr(da_s), self.g('conv1_s.weight'), N, Ci, T, H, W, C0, C0p,
+                 self.dt, st)
+
+    # ------------------------------------------------------------------ bottleneck
+    def block_fwd(self, blk, x, geom, training, save_list):
+        lib, st, dt = self.lib, self._stream(), self.dt
+        N, T, H, W = geom
+        pre = blk.prefix
+        s = blk.stride
+        Cin, Cm, Co = blk.in_planes, blk.mid_planes, blk.out_planes
+        Cinp, Cmp, Cop = pad8(Cin), pad8(Cm), pad8(Co)
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        P_in, P_out = T * H * W, T * Ho * Wo
+        af = self.arena_f
+        # conv1 + bn1 statistics
+        a1 = self._act(N, T, H, W, Cmp)
+        st1 = self._stats(af, N, Cmp) if training else None
+        lib.call('x3d_pwconv_fwd', _ptr(x), self.pk(pre + '.conv1.f'), _ptr(a1), N, T, H, W, Cinp, Cmp, 1,
+                 _ptr(st1), dt, st)
+        bn1 = self._bn_forward_state(blk.bn1, pre + '.bn1', st1, N, P_in, Cm, Cmp, training)
+        # depthwise conv2 on relu(bn1(a1)); statistics for bn2 and the SE pool
+        a2 = self._act(N, T, Ho, Wo, Cmp)
+        need2 = training or blk.has_se
+        st2 = self._stats(af, N, Cmp) if need2 else None
+        lib.call('x3d_dwconv_fwd', _ptr(a1), self.pk(pre + '.conv2.d'), _ptr(a2), N, T, H, W, Cmp, 3, 3, 3, s,
+                 _ptr(bn1.scale), _ptr(bn1.shift), bn1.splits, 1, _ptr(st2), dt, st)
+        bn2 = self._bn_forward_state(blk.bn2, pre + '.bn2', st2, N, P_out, Cm, Cmp, training)
+        pooled = hidden = gate = None
+        if blk.has_se:
+            sw = blk.se_width
+            pooled, hidden, gate = self._f32(N, Cm), self._f32(N, sw), self._f32(N, Cmp)
+            lib.call('x3d_se_fwd', _ptr(st2), _ptr(bn2.scale), _ptr(bn2.shift), bn2.splits, N, P_out, Cm, Cmp, sw,
+                     self.p(pre + '.fc1.weight'), self.p(pre + '.fc1.bias'), self.p(pre + '.fc2.weight'),
+                     self.p(pre + '.fc2.bias'), _ptr(pooled), _ptr(hidden), _ptr(gate), st)
+        v = self._act(N, T, Ho, Wo, Cmp)
+        lib.call('x3d_swish_gate_fwd', _ptr(a2), _ptr(bn2.scale), _ptr(bn2.shift), bn2.splits, _ptr(gate), _ptr(v),
+                 N, P_out, Cmp, dt, st)
+        # conv3 + bn3
+        a3 = self._act(N, T, Ho, Wo, Cop)
+        st3 = self._stats(af, N, Cop) if training else None
+        lib.call('x3d_pwconv_fwd', _ptr(v), self.pk(pre + '.conv3.f'), _ptr(a3), N, T, Ho, Wo, Cmp, Cop, 1,
+                 _ptr(st3), dt, st)
+        bn3 = self._bn_forward_state(blk.bn3, pre + '.bn3', st3, N, P_out, Co, Cop, training)
+        out = self._act(N, T, Ho, Wo, Cop)
+        ad = bnd = None
+        if blk.downsample is not None:
+            ad = self._act(N, T, Ho, Wo, Cop)
+            std = self._stats(af, N, Cop) if training else None
+            lib.call('x3d_pwconv_fwd', _ptr(x), self.pk(pre + '.downsample.0.f'), _ptr(ad), N, T, H, W, Cinp, Cop, s,
+                     _ptr(std), dt, st)
+            bnd = self._bn_forward_state(blk.downsample[1], pre + '.downsample.1', std, N, P_out, Co, Cop, training)
+            lib.call('x3d_bn_act_fwd', _ptr(a3), _ptr(bn3.scale), _ptr(bn3.shift), bn3.splits, _ptr(ad),
+                     _ptr(bnd.scale), _ptr(bnd.shift), 1, _ptr(out), N, P_out, Cop, dt, st)
+        else:
+            lib.call('x3d_bn_act_fwd', _ptr(a3), _ptr(bn3.scale), _ptr(bn3.shift), bn3.splits, _ptr(x), None, None,
+                     1, _ptr(out), N, P_out, Cop, dt, st)
+        if save_list is not None:
+            save_list.append((blk, geom, x, a1, bn1, a2, st2, bn2, pooled, hidden, gate, v, a3, bn3, ad, bnd, out))
+        return out, (N, T, Ho, Wo)
+
+    def block_bwd(self, rec, dout, need_dx=True):
+        lib, st, dt = self.lib, self._stream(), self.dt
+        (blk, geom, x, a1, bn1, a2, st2, bn2, pooled, hidden, gate, v, a3, bn3, ad, bnd, out) = rec
+        N, T, H, W = geom
+        pre = blk.prefix
+        s = blk.stride
+        Cin, Cm, Co = blk.in_planes, blk.mid_planes, blk.out_planes
+        Cinp, Cmp, Cop = pad8(Cin), pad8(Cm), pad8(Co)
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        P_in, P_out = T * H * W, T * Ho * Wo
+        ab = self.arena_b
+        # ---- bn3 backward (dpre = dout * [out > 0])
+        da3 = self._act(N, T, Ho, Wo, Cop)
+        self._bn_backward(ab, pre + '.bn3', bn3, dout, out, a3, N, P_out, Co, Cop, da3)
+        # ---- conv3
+        lib.call('x3d_pwconv_wgrad', _ptr(v), _ptr(da3), self.g(pre + '.conv3.weight'), N, T, Ho, Wo, Cm, Cmp, Co,
+                 Cop, 1, dt, st)
+        dv = self._act(N, T, Ho, Wo, Cmp)
+        lib.call('x3d_pwconv_dgrad', _ptr(da3), self.pk(pre + '.conv3.t'), _ptr(dv), N, T, Ho, Wo, Cmp, Cop, 1, 0,
+                 dt, st)
+        del da3
+        # ---- swish, SE gate, bn2
+        bst2 = self._stats(ab, N, Cmp)
+        lib.call('x3d_swish_gate_bwd_reduce', _ptr(dv), _ptr(a2), _ptr(bn2.scale), _ptr(bn2.shift), bn2.splits,
+                 _ptr(gate), _ptr(bst2), N, P_out, Cmp, dt, st)
+        coef2, work = self._f32(N, Cmp, 3), self._f32(N, Cmp)
+        if blk.has_se:
+            se_args = (self.p(pre + '.fc1.weight'), self.p(pre + '.fc2.weight'), _ptr(pooled), _ptr(hidden), _ptr(gate),
+                       self.g(pre + '.fc1.weight'), self.g(pre + '.fc1.bias'), self.g(pre + '.fc2.weight'),
+                       self.g(pre + '.fc2.bias'))
+            sw = blk.se_width
+        else:
+            se_args = (None,) * 9
+            sw = 0
+        fwd_stats = st2 if st2 is not None else bst2   # only dereferenced when the block has SE
+        lib.call('x3d_se_bn_bwd', _ptr(fwd_stats), _ptr(bst2), N, bn2.splits, P_out, Cm, Cmp, sw,
+                 self.p(pre + '.bn2.weight'), _ptr(bn2.mean), _ptr(bn2.rstd), _ptr(bn2.scale), _ptr(bn2.shift),
+                 int(bn2.train), *se_args, self.g(pre + '.bn2.weight'), self.g(pre + '.bn2.bias'), _ptr(work),
+                 _ptr(coef2), st)
+        da2 = dv   # in place
+        lib.call('x3d_swish_gate_bwd_apply', _ptr(dv), _ptr(a2), _ptr(bn2.scale), _ptr(bn2.shift), bn2.splits,
+                 _ptr(gate), _ptr(coef2), _ptr(da2), N, P_out, Cmp, dt, st)
+        # ---- depthwise conv2
+        lib.call('x3d_dwconv_wgrad', _ptr(a1), _ptr(da2), self.g(pre + '.conv2.weight'), N, T, H, W, Cm, Cmp, 3, 3, 3,
+                 s, _ptr(bn1.scale), _ptr(bn1.shift), bn1.splits, 1, dt, st)
+        d1 = self._act(N, T, H, W, Cmp)
+        bst1 = self._stats(ab, N, Cmp)
+        lib.call('x3d_dwconv_dgrad', _ptr(da2), self.pk(pre + '.conv2.d'), _ptr(d1), N, T, H, W, Cmp, 3, 3, 3, s,
+                 _ptr(a1), _ptr(bn1.scale), _ptr(bn1.shift), bn1.splits, _ptr(bst1), dt, st)
+        del dv, da2
+        # ---- bn1 (relu mask already applied by the dgrad epilogue)
+        coef1 = self._f32(3, bn1.splits, Cmp)
+        lib.call('x3d_bn_bwd_finalize', _ptr(bst1), N, bn1.splits, P_in, Cm, Cmp, self.p(pre + '.bn1.weight'),
+                 _ptr(bn1.mean), _ptr(bn1.rstd), int(bn1.train), _ptr(coef1), self.g(pre + '.bn1.weight'),
+                 self.g(pre + '.bn1.bias'), st)
+        da1 = d1
+        lib.call('x3d_bn_bwd_apply', _ptr(d1), None, _ptr(a1), _ptr(coef1), bn1.splits, _ptr(da1), N, P_in, Cmp, dt, st)
+        # ---- conv1
+        lib.call('x3d_pwconv_wgrad', _ptr(x), _ptr(da1), self.g(pre + '.conv1.weight'), N, T, H, W, Cin, Cinp, Cm, Cmp,
+                 1, dt, st)
+        dx = None
+        if need_dx:
+            dx = self._act(N, T, H, W, Cinp)
+            lib.call('x3d_pwconv_dgrad', _ptr(da1), self.pk(pre + '.conv1.t'), _ptr(dx), N, T, H, W, Cinp, Cmp, 1, 0,
+                     dt, st)
+        # ---- residual branch
+        if blk.downsample is not None:
+            dad = self._act(N, T, Ho, Wo, Cop)
+            self._bn_backward(ab, pre + '.downsample.1', bnd, dout, out, ad, N, P_out, Co, Cop, dad)
+            lib.call('x3d_pwconv_wgrad', _ptr(x), _ptr(dad), self.g(pre + '.downsample.0.weight'), N, T, H, W, Cin,
+                     Cinp, Co, Cop, s, dt, st)
+            if need_dx:
+                lib.call('x3d_pwconv_dgrad', _ptr(dad), self.pk(pre + '.downsample.0.t'), _ptr(dx), N, T, H, W, Cinp,
+                         Cop, s, 1, dt, st)
+        elif need_dx:
+            lib.call('x3d_relu_bwd_add', _ptr(dout), _ptr(out), _ptr(dx), dx.numel(), dt, st)
+        return dx
+
+    # ------------------------------------------------------------------ head
+    def _head_fwd(self, xL, geom, training, dropout_mask, save):
+        m, lib, st, dt = self.model, self.lib, self._stream(), self.dt
+        N, T, H, W = geom
+        C5in, C5 = m.conv5.in_channels, m.conv5.out_channels
+        C5inp, C5p = pad8(C5in), pad8(C5)
+        P = T * H * W
+        a5 = self._act(N, T, H, W, C5p)
+        st5 = self._stats(self.arena_f, N, C5p) if training else None
+        lib.call('x3d_pwconv_fwd', _ptr(xL), self.pk('conv5.f'), _ptr(a5), N, T, H, W, C5inp, C5p, 1, _ptr(st5), dt, st)
+        bn5 = self._bn_forward_state(m.bn5, 'bn5', st5, N, P, C5, C5p, training)
+        pool_t = 1 if m.task == 'class' else 0
+        R = N if pool_t else N * T
+        pooled = self._f32(R, C5)
+        lib.call('x3d_bn_relu_pool_fwd', _ptr(a5), _ptr(bn5.scale), _ptr(bn5.shift), bn5.splits, _ptr(pooled), N, T,
+                 H * W, pool_t, C5, C5p, dt, st)
+        F1 = m.fc1.out_channels
+        h1 = self._f32(R, F1)
+        lib.call('x3d_small_gemm', _ptr(pooled), C5, 1, self.p('fc1.weight'), 1, C5, _ptr(h1), F1, R, F1, C5, None, 1,
+                 _ptr(dropout_mask), 0, st)
+        ncls = m.fc2.out_features
+        logits = self._f32(R, ncls)
+        lib.call('x3d_small_gemm', _ptr(h1), F1, 1, self.p('fc2.weight'), 1, F1, _ptr(logits), ncls, R, ncls, F1,
+                 self.p('fc2.bias'), 0, None, 0, st)
+        if save is not None:
+            save['head'] = (xL, geom, a5, bn5, pooled, h1, dropout_mask)
+        if pool_t:
+            return logits.view(N, ncls, 1)
+        return logits.view(N, T, ncls).permute(0, 2, 1)
+
+    def _head_bwd(self, save, dlogits):
+        m, lib, st, dt = self.model, self.lib, self._stream(), self.dt
+        xL, geom, a5, bn5, pooled, h1, dropout_mask = save['head']
+        N, T, H, W = geom
+        C5in, C5 = m.conv5.in_channels, m.conv5.out_channels
+        C5inp, C5p = pad8(C5in), pad8(C5)
+        P = T * H * W
+        pool_t = 1 if m.task == 'class' else 0
+        R = N if pool_t else N * T
+        F1 = m.fc1.out_channels
+        ncls = m.fc2.out_features
+        if pool_t:
+            dl = dlogits.reshape(N, ncls)
+        else:
+            dl = dlogits.permute(0, 2, 1).reshape(R, ncls)
+        dl = dl.to(torch.float32).contiguous()
+        # fc2
+        lib.call('x3d_small_gemm', _ptr(dl), 1, ncls, _ptr(h1), F1, 1, self.g('fc2.weight'), F1, ncls, F1, R, None, 0,
+                 None, 1, st)
+        lib.call('x3d_colsum', _ptr(dl), R, ncls, self.g('fc2.bias'), st)
+        dh = self._f32(R, F1)
+        lib.call('x3d_small_gemm', _ptr(dl), ncls, 1, self.p('fc2.weight'), F1, 1, _ptr(dh), F1, R, F1, ncls, None, 0,
+                 None, 0, st)
+        dz = dh
+        lib.call('x3d_relu_mask_mul', _ptr(dh), _ptr(h1), _ptr(dropout_mask), _ptr(dz), R * F1, st)
+        # fc1
+        lib.call('x3d_small_gemm', _ptr(dz), 1, F1, _ptr(pooled), C5, 1, self.g('fc1.weight'), C5, F1, C5, R, None, 0,
+                 None, 1, st)
+        dpooled = self._f32(R, C5)
+        lib.call('x3d_small_gemm', _ptr(dz), F1, 1, self.p('fc1.weight'), C5, 1, _ptr(dpooled), C5, R, C5, F1, None, 0,
+                 None, 0, st)
+        # relu + pool + bn5
+        bst5 = self._stats(self.arena_b, N, C5p)
+        lib.call('x3d_bn_relu_pool_bwd_reduce', _ptr(a5), _ptr(bn5.scale), _ptr(bn5.shift), bn5.splits, _ptr(dpooled),
+                 _ptr(bst5), N, T, H * W, pool_t, C5, C5p, dt, st)
+        coef5 = self._f32(3, bn5.splits, C5p)
+        lib.call('x3d_bn_bwd_finalize', _ptr(bst5), N, bn5.splits, P, C5, C5p, self.p('bn5.weight'), _ptr(bn5.mean),
+                 _ptr(bn5.rstd), int(bn5.train), _ptr(coef5), self.g('bn5.weight'), self.g('bn5.bias'), st)
+        da5 = self._act(N, T, H, W, C5p)
+        lib.call('x3d_bn_relu_pool_bwd_apply', _ptr(a5), _ptr(bn5.scale), _ptr(bn5.shift), bn5.splits, _ptr(dpooled),
+                 _ptr(coef5), _ptr(da5), N, T, H * W, pool_t, C5, C5p, dt, st)
+        # conv5
+        lib.call('x3d_pwconv_wgrad', _ptr(xL), _ptr(da5), self.g('conv5.weight'), N, T, H, W, C5in, C5inp, C5, C5p, 1,
+                 dt, st)
+        dxL = self._act(N, T, H, W, C5inp)
+        lib.call('x3d_pwconv_dgrad', _ptr(da5), self.pk('conv5.t'), _ptr(dxL), N, T, H, W, C5inp, C5p, 1, 0, dt, st)
+        return dxL
+
+    # ------------------------------------------------------------------ whole network
+    def forward(self, x: torch.Tensor, training: bool, need_grad: bool,
+                dropout_mask: Optional[torch.Tensor] = None):
+        """x: [B,3,T,H,W] fp32 NCDHW on CUDA -> logits ([B,C,1] or [B,C,T], fp32), saved state."""
+        if not x.is_cuda:
+            raise RuntimeError('x3d_multigrid_b200 runs on CUDA only (no CPU fallback)')
+        if x.dtype != torch.float32:
+            raise RuntimeError('input clips must be fp32 NCDHW (x3d.py:316)')
+        x = x.contiguous()
+        self.prepare(x.device)
+        self.arena_f.begin()
+        self.pack_weights()
+        save = {'blocks': []} if need_grad else None
+        h, geom = self._stem_fwd(x, training, save)
+        for blk in self.model.blocks():
+            h, geom = self.block_fwd(blk, h, geom, training, save['blocks'] if save is not None else None)
+        logits = self._head_fwd(h, geom, training, dropout_mask, save)
+        return logits, save
+
+    def backward(self, save, dlogits: torch.Tensor):
+        """Accumulates parameter gradients into ``self.gflat`` (zeroed here first)."""
+        self.arena_b.begin()
+        self.new_grad_buffer()
+        d = self._head_bwd(save, dlogits)
+        blocks = save['blocks']
+        stage_of = [rec[0].stage for rec in blocks]
+        for i in range(len(blocks) - 1, -1, -1):
+            d = self.block_bwd(blocks[i], d)
+            blocks[i] = None
+            # bucket b (0 = head+stage4, 1 = stage3, 2 = stage2) is final once its first block is done
+            if self.grad_hook and (i == 0 or stage_of[i - 1] != stage_of[i]) and stage_of[i] > 1:
+                self.grad_hook(4 - stage_of[i])
+        self._stem_bwd(save, d)
+        if self.grad_hook:
+            self.grad_hook(3)
+        return self.param_grads()
