@@ -77,9 +77,21 @@ class Lib:
             f.argtypes = argtypes
             self.fn[name] = f
         self._err = self.fn['x3d_last_error']
+        # optional per-kernel timing (bench.py): CUDA events around the calls named in prof_names,
+        # recorded on torch's current stream, which is the stream every call is launched on
+        self.prof_names = set()
+        self.prof_records = []
 
     def call(self, name: str, *args):
-        rc = self.fn[name](*args)
+        if name in self.prof_names:
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = self.fn[name](*args)
+            e1.record()
+            self.prof_records.append((name, args, e0, e1))
+        else:
+            rc = self.fn[name](*args)
         if rc != 0:
             raise RuntimeError(f'{name} failed (rc={rc}): {self._err().decode()}')
 

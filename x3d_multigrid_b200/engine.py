@@ -216,8 +216,14 @@ class Engine:
         return self.refs[name].param.data_ptr()
 
     def new_grad_buffer(self):
-        """fresh zeroed flat gradient buffer (the previous one may be owned by .grad views)"""
-        self.gflat = torch.zeros(self.gflat_numel, dtype=torch.float32, device=self.device)
+        """Zeroed flat gradient buffer for this backward pass.  The persistent buffer is reused
+        (stable addresses: fused optimizer tables and CUDA graphs stay valid) unless some
+        parameter still holds a .grad -- then the caller is accumulating and the old buffer may
+        be aliased by those .grad views, so a fresh one is taken."""
+        if any(r.param.grad is not None for r in self.param_order):
+            self.gflat = torch.zeros(self.gflat_numel, dtype=torch.float32, device=self.device)
+        else:
+            self.gflat.zero_()
 
     def param_grads(self):
         return [self.gflat[r.goff:r.goff + r.numel].view(r.param.shape) for r in self.param_order]
