@@ -105,6 +105,10 @@ DW_CASES = [  # N, C, T, H, W, stride, kernel
     (2, 24, 5, 6, 5, 1, (5, 1, 1)),
     (1, 432, 4, 4, 4, 1, (3, 3, 3)),
     (2, 16, 13, 20, 12, 1, (3, 3, 3)),
+    (2, 56, 3, 20, 37, 1, (3, 3, 3)),     # several ragged tiles of the tiled kernel
+    (2, 56, 2, 21, 35, 2, (3, 3, 3)),
+    (1, 216, 2, 14, 14, 1, (3, 3, 3)),    # channel chunks that do not divide Cp evenly
+    (2, 630, 2, 10, 10, 1, (3, 3, 3)),    # X3D-XL stage 4 (Cp = 632)
 ]
 
 
