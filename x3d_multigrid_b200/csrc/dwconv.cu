@@ -12,6 +12,10 @@ namespace x3d {
 int dwconv_fwd_tiled(const void* x, const float* w_packed, void* y, int64_t N, int64_t T, int64_t H, int64_t W,
                      int64_t Cp, int stride, const float* in_scale, const float* in_shift, int splits, int relu_in,
                      double* stats, x3d_dtype_t dt, cudaStream_t stream, bool* handled);
+int dwconv_dgrad_tiled(const void* dy, const float* w_packed, void* dx, int64_t N, int64_t T, int64_t H, int64_t W,
+                       int64_t Cp, int stride, const void* mask_src, const float* mask_scale,
+                       const float* mask_shift, int splits, double* stats, x3d_dtype_t dt, cudaStream_t stream,
+                       bool* handled);
 }
 
 struct DwGeom {
@@ -239,7 +243,13 @@ extern "C" int x3d_dwconv_dgrad(const void* dy, const float* w_packed, void* dx,
   g.Wo = (int)((W + 2 * (kw / 2) - kw) / stride + 1);
   const int64_t P = T_ * H * W;
   if (N * P == 0) return 0;
-#define L_(KT_, KH_, KW_, MK)                                                                                   \
+  if (kt == 3) {
+    bool handled = false;
+    int rc = dwconv_dgrad_tiled(dy, w_packed, dx, N, T_, H, W, Cp, stride, mask_src, mask_scale, mask_shift, splits,
+                                stats, dt, as_stream(stream), &handled);
+    if (handled) return rc;
+  }
+#define L_(KT_, KH_, KW_, MK)                                                                                \
   dw_dgrad_direct_kernel<T, KT_, KH_, KW_, MK><<<grid, rg.threads, smem, as_stream(stream)>>>(                  \
       (const T*)dy, w_packed, (T*)dx, g, (const T*)mask_src, mask_scale, mask_shift, splits, stats, P, rg.cv,   \
       rg.rows, rg.chunk)

@@ -1,0 +1,524 @@
+// Tiled depthwise 3x3x3 forward AND dgrad for the hot shapes (stride (1,1,1) / (1,2,2), pad 1), NDHWC.
+//
+// Design (see DESIGN.md "dwconv"):
+//  * CTA = (sample n, TH x TW output tile, chunk of CC channels), marching over ALL T planes.
+//    Each input plane tile (with its halo) is brought ONCE into shared memory by TMA
+//    (cp.async.bulk.tensor.5d, one instruction issued by one thread per plane, completion on an
+//    mbarrier) into a 3-deep ring: two planes are in flight while one is consumed.
+//  * thread = (channel PAIR, 2 x PW output patch).  The 27 taps of the pair live in registers as float2;
+//    every shared-memory word (2 channels) feeds up to 27 packed FFMA2 (fma.rn.f32x2): one input plane
+//    contributes to three output planes held in register accumulators whose roles rotate by a 3x
+//    unrolled plane loop (no register moves).  CC and TW are template parameters so that every window
+//    LDS uses an immediate offset (no address arithmetic in the inner loop).
+//  * four tap mappings share the kernel (template MODE): forward stride 1 / 2, and dgrad stride 1 / 2
+//    (dgrad s1 = correlation with the flipped taps; dgrad s2 gathers, per output parity, only the taps
+//    that hit a sampled position: 6.75 FMA per dx element instead of 27).
+//  * forward: the preceding SubBatchNorm3d+ReLU (scale/shift per (split,channel)) is applied on the fly
+//    to the window values.  Zero padding must be applied AFTER that transform (x3d.py:147-150): the
+//    tensor map fills out-of-image halo elements with NaN (CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_
+//    ZERO_FMA) and relu is fmaxf(v, 0), which returns the non-NaN operand -- padded taps become exact
+//    zeros without any select in the inner loop.  Without the fused transform the OOB fill is zero.
+//  * forward epilogue: store + per-(sample,channel) sum / sum-of-squares of the stored values (bn2
+//    statistics and the SE global pool).  dgrad epilogue: ReLU mask of the preceding BN+ReLU recomputed
+//    from the saved conv1 output (aux), store, and the two BN-backward sums (sum d, sum d*aux).
+//    Both: shared atomics -> one fp64 atomic per channel per CTA.
+// Arithmetic intensity of the stride-1 forward in bf16 is 27 FMA / 4 B = 6.75 FMA/B, above the B200
+// balance of ~5.7 FMA/B (37 TFMA/s fp32 vs 6.5 TB/s): those layers are bound by the fp32 FMA pipe, which
+// is why the inner loop is FFMA2 and everything else is kept off that pipe.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "dwconv_tiled.h"
+
+using namespace x3d;
+
+namespace {
+
+constexpr int PH = 2;             // output patch per thread: PH x PW
+constexpr int NSTAGE = 3;         // input-plane ring
+template <int PW> struct Cfg { static constexpr int MAXT = PW == 4 ? 384 : 256, MINB = PW == 4 ? 1 : 2; };
+
+enum { M_FWD1 = 0, M_FWD2 = 1, M_DG1 = 2, M_DG2 = 3 };
+// geometry of the four tap mappings; "out" = tensor being produced, "in" = tensor staged through smem
+template <int MODE>
+struct Map {
+  static constexpr bool DG = MODE >= 2;
+  // input extent needed for an output extent of n
+  __host__ __device__ static constexpr int in_ext(int n) {
+    return MODE == M_FWD1 ? n + 2 : MODE == M_FWD2 ? (n - 1) * 2 + 3 : MODE == M_DG1 ? n + 2 : n / 2 + 1;
+  }
+  // input coordinate of the first staged row/col for an output tile starting at o0
+  __host__ __device__ static constexpr int in_org(int o0) {
+    return MODE == M_FWD1 ? o0 - 1 : MODE == M_FWD2 ? o0 * 2 - 1 : MODE == M_DG1 ? o0 - 1 : o0 / 2;
+  }
+  // offset (in input positions) of a patch window that starts p output positions into the tile
+  __host__ __device__ static constexpr int win_off(int p) {
+    return MODE == M_FWD1 ? p : MODE == M_FWD2 ? p * 2 : MODE == M_DG1 ? p : p / 2;
+  }
+  // spatial tap index used by window element r for patch output o (valid iff in [0,2])
+  __host__ __device__ static constexpr int tap(int r, int o) {
+    return MODE == M_FWD1 ? r - o : MODE == M_FWD2 ? r - 2 * o : MODE == M_DG1 ? o - r + 2 : o + 1 - 2 * r;
+  }
+  // temporal tap used for the output planes tin+1 / tin / tin-1
+  static constexpr int KT_NEW = DG ? 2 : 0, KT_MID = 1, KT_OLD = DG ? 0 : 2;
+};
+
+// ---- mbarrier / TMA primitives -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ float2 unpack_pair(uint32_t w0, uint32_t w1);
+template <typename T>
+__device__ __forceinline__ float2 lds_pair(const T* p);
+template <>
+__device__ __forceinline__ float2 lds_pair<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <>
+__device__ __forceinline__ float2 lds_pair<float>(const float* p) {
+  return *reinterpret_cast<const float2*>(p);
+}
+// predicated global load of a channel pair (0 when off)
+template <typename T>
+__device__ __forceinline__ float2 ldg_pair_if(const T* p, uint32_t pred);
+template <>
+__device__ __forceinline__ float2 ldg_pair_if<__nv_bfloat16>(const __nv_bfloat16* p, uint32_t pred) {
+  uint32_t w = 0;
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p ld.global.nc.b32 %0, [%1];\n}\n" : "+r"(w) : "l"(p), "r"(pred));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <>
+__device__ __forceinline__ float2 ldg_pair_if<float>(const float* p, uint32_t pred) {
+  float2 v = make_float2(0.f, 0.f);
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %3, 0;\n@p ld.global.nc.v2.f32 {%0, %1}, [%2];\n}\n"
+               : "+f"(v.x), "+f"(v.y)
+               : "l"(p), "r"(pred));
+  return v;
+}
+// predicated store of a channel pair; returns the values as stored (for the statistics)
+template <typename T>
+__device__ __forceinline__ float2 st_pair_if(T* p, float2 v, uint32_t pred);
+template <>
+__device__ __forceinline__ float2 st_pair_if<__nv_bfloat16>(__nv_bfloat16* p, float2 v, uint32_t pred) {
+  const uint32_t w = pack_bf16x2(v.x, v.y);
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.global.b32 [%0], %1;\n}\n" ::"l"(p), "r"(w), "r"(pred) : "memory");
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <>
+__device__ __forceinline__ float2 st_pair_if<float>(float* p, float2 v, uint32_t pred) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %3, 0;\n@p st.global.v2.f32 [%0], {%1, %2};\n}\n" ::"l"(p), "f"(v.x), "f"(v.y),
+               "r"(pred)
+               : "memory");
+  return v;
+}
+
+struct TileGeom {
+  int T, Ho, Wo, Cp;     // extents of the tensor being PRODUCED (y for forward, dx for dgrad)
+  int TH;                // output tile height (TW and CC are template parameters)
+  int tiles_w;
+  int stage_elems;       // ring-slot stride in elements (128-byte aligned)
+};
+
+// XF: fused relu(x*scale+shift) on the staged input (forward modes)
+// AUX: dgrad epilogue with the ReLU mask / BN sums from the saved conv1 output
+template <typename T, int MODE, int CC, int TW, int PW, bool XF, bool AUX>
+__global__ void __launch_bounds__(Cfg<PW>::MAXT, Cfg<PW>::MINB)
+dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w, T* __restrict__ y,
+                 const TileGeom g, const float* __restrict__ scale, const float* __restrict__ shift, int splits,
+                 const T* __restrict__ aux, double* __restrict__ stats) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using M = Map<MODE>;
+  constexpr int WR = M::in_ext(PH), WC = M::in_ext(PW);         // per-thread input window
+  constexpr int IW = M::in_ext(TW);                              // CTA input tile width (with halo)
+  constexpr int ROW = IW * CC;                                   // smem row stride (elements)
+  constexpr int PAIRS = CC / 2;
+  constexpr int PPR = TW / PW;                                   // patches per tile row
+  constexpr int NO = PH * PW;
+  const int IH = M::in_ext(g.TH);
+  const int Cp = g.Cp;
+  T* const sbuf = reinterpret_cast<T*>(smem_raw);               // NSTAGE plane buffers (ring)
+  float* s_stat = reinterpret_cast<float*>(sbuf + NSTAGE * g.stage_elems);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stat + 2 * CC);
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int ho0 = (blockIdx.x / g.tiles_w) * g.TH, wo0 = (blockIdx.x % g.tiles_w) * TW;
+  const int cbase = blockIdx.y * CC;
+  const int n = blockIdx.z;
+  const int pair = tid % PAIRS, patch = tid / PAIRS;
+  const int py = patch / PPR, px = patch % PPR;
+  const int c = cbase + 2 * pair;
+  const bool ch_ok = c < Cp;
+  const int hi0 = M::in_org(ho0), wi0 = M::in_org(wo0);
+  const int nT = g.T;
+  const uint32_t plane_bytes = (uint32_t)(IH * ROW * sizeof(T));
+
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < NSTAGE; ++k) mbar_init(&full_bar[k], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int t, int slot) {      // one thread: arm the barrier, fire one TMA box load
+    mbar_expect_tx(&full_bar[slot], plane_bytes);
+    tma_load_5d(sbuf + slot * g.stage_elems, &tmap, &full_bar[slot], cbase, wi0, hi0, t, n);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < NSTAGE - 1; ++k)
+      if (k < nT) issue(k, k);
+  }
+
+  // ---- per-thread constants ----------------------------------------------------------------
+  float2 wreg[27];
+#pragma unroll
+  for (int tap = 0; tap < 27; ++tap)
+    wreg[tap] = ch_ok ? *reinterpret_cast<const float2*>(w + (int64_t)tap * Cp + c) : make_float2(0.f, 0.f);
+  float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+  if ((XF || AUX) && ch_ok) {
+    const int b = n % splits;
+    sc = *reinterpret_cast<const float2*>(scale + (int64_t)b * Cp + c);
+    sh = *reinterpret_cast<const float2*>(shift + (int64_t)b * Cp + c);
+  }
+  const int win_base = (M::win_off(py * PH) * IW + M::win_off(px * PW)) * CC + 2 * pair;
+
+  float2 accA[NO], accB[NO], accC[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) accA[o] = accB[o] = accC[o] = make_float2(0.f, 0.f);
+  float2 ssum = make_float2(0.f, 0.f), ssq = make_float2(0.f, 0.f);
+
+  const int ho_t = ho0 + py * PH, wo_t = wo0 + px * PW;
+  uint32_t omask = 0;                      // validity of the patch outputs (bit oy*PW+ox)
+#pragma unroll
+  for (int oy = 0; oy < PH; ++oy)
+#pragma unroll
+    for (int ox = 0; ox < PW; ++ox)
+      if (ch_ok && ho_t + oy < g.Ho && wo_t + ox < g.Wo) omask |= 1u << (oy * PW + ox);
+  const int out_plane = g.Ho * g.Wo * Cp;  // < 2^31 elements (checked on the host)
+  const int orow = g.Wo * Cp;
+  const int64_t out0 = ((int64_t)n * nT * g.Ho + ho_t) * (int64_t)orow + (int64_t)wo_t * Cp + c;   // plane 0
+  T* yp = y + out0;
+  const T* ap = AUX ? aux + out0 : nullptr;
+  float2 av[NO];                           // aux values of the plane stored next (dgrad epilogue)
+
+  // store a finished accumulator as the next output plane (planes are finished in order 0,1,2,...)
+  auto store_plane = [&](float2 (&a)[NO]) {
+#pragma unroll
+    for (int oy = 0; oy < PH; ++oy) {
+#pragma unroll
+      for (int ox = 0; ox < PW; ++ox) {
+        const int o = oy * PW + ox;
+        const uint32_t ok = omask & (1u << o);
+        float2 v = a[o];
+        if (AUX) {                          // d = dgrad * [relu(bn(aux)) > 0]
+          const float2 t = __ffma2_rn(av[o], sc, sh);
+          v.x = t.x > 0.f ? v.x : 0.f;
+          v.y = t.y > 0.f ? v.y : 0.f;
+        }
+        float2 r = st_pair_if<T>(yp + oy * orow + ox * Cp, v, ok);
+        if (!ok) r = make_float2(0.f, 0.f);
+        ssum.x += r.x; ssum.y += r.y;
+        ssq = __ffma2_rn(r, AUX ? av[o] : r, ssq);
+        a[o] = make_float2(0.f, 0.f);
+      }
+    }
+    yp += out_plane;
+  };
+  auto load_aux = [&]() {
+    if (AUX) {
+#pragma unroll
+      for (int oy = 0; oy < PH; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < PW; ++ox)
+          av[oy * PW + ox] = ldg_pair_if<T>(ap + oy * orow + ox * Cp, omask & (1u << (oy * PW + ox)));
+      ap += out_plane;
+    }
+  };
+
+  // One plane: input plane `tin` feeds output planes tin+1 (accumulator `nw`), tin (`md`) and tin-1
+  // (`od`), which is complete afterwards and is stored.
+  int slot = 0;
+  uint32_t parity = 0;
+  auto plane = [&](int tin, float2 (&nw)[NO], float2 (&md)[NO], float2 (&od)[NO]) {
+    mbar_wait(&full_bar[slot], parity);    // TMA bytes of plane tin have landed
+    __syncthreads();                       // everybody is done with plane tin-1: its ring slot is free
+    if (tid == 0) {
+      const int tn = tin + NSTAGE - 1;
+      int sn = slot + NSTAGE - 1;
+      if (sn >= NSTAGE) sn -= NSTAGE;
+      if (tn < nT) issue(tn, sn);
+    }
+    if (tin >= 1) load_aux();              // aux of output plane tin-1, consumed after the FMA phase
+    const T* bp = sbuf + slot * g.stage_elems + win_base;
+    if (++slot == NSTAGE) { slot = 0; parity ^= 1u; }
+#pragma unroll
+    for (int r = 0; r < WR; ++r) {
+#pragma unroll
+      for (int cc = 0; cc < WC; ++cc) {
+        float2 xv = lds_pair<T>(bp + r * ROW + cc * CC);
+        if (XF) {
+          xv = __ffma2_rn(xv, sc, sh);
+          xv.x = fmaxf(xv.x, 0.f);          // also maps the NaN halo to exact zero
+          xv.y = fmaxf(xv.y, 0.f);
+        }
+#pragma unroll
+        for (int oy = 0; oy < PH; ++oy) {
+          const int kh = M::tap(r, oy);
+          if (kh < 0 || kh > 2) continue;
+#pragma unroll
+          for (int ox = 0; ox < PW; ++ox) {
+            const int kw = M::tap(cc, ox);
+            if (kw < 0 || kw > 2) continue;
+            const int o = oy * PW + ox, tap = kh * 3 + kw;
+            nw[o] = __ffma2_rn(wreg[M::KT_NEW * 9 + tap], xv, nw[o]);
+            md[o] = __ffma2_rn(wreg[M::KT_MID * 9 + tap], xv, md[o]);
+            od[o] = __ffma2_rn(wreg[M::KT_OLD * 9 + tap], xv, od[o]);
+          }
+        }
+      }
+    }
+    if (tin >= 1) store_plane(od);
+    else {
+#pragma unroll
+      for (int o = 0; o < NO; ++o) od[o] = make_float2(0.f, 0.f);
+    }
+  };
+
+  int tin = 0;
+  for (; tin + 3 <= nT; tin += 3) {
+    plane(tin, accA, accB, accC);
+    plane(tin + 1, accC, accA, accB);
+    plane(tin + 2, accB, accC, accA);
+  }
+  // remainder; the last executed plane's `md` accumulator holds output plane T-1
+  const int rem = nT - tin;
+  if (rem == 0) {
+    load_aux();
+    store_plane(accC);                     // last call was plane(.., accB, accC, accA): md = accC
+  } else if (rem == 1) {
+    plane(tin, accA, accB, accC);
+    load_aux();
+    store_plane(accB);
+  } else {
+    plane(tin, accA, accB, accC);
+    plane(tin + 1, accC, accA, accB);
+    load_aux();
+    store_plane(accA);
+  }
+
+  if (stats != nullptr) {
+    __syncthreads();
+    for (int i = tid; i < CC * 2; i += nthr) s_stat[i] = 0.f;
+    __syncthreads();
+    atomicAdd(&s_stat[(2 * pair) * 2 + 0], ssum.x);
+    atomicAdd(&s_stat[(2 * pair) * 2 + 1], ssq.x);
+    atomicAdd(&s_stat[(2 * pair + 1) * 2 + 0], ssum.y);
+    atomicAdd(&s_stat[(2 * pair + 1) * 2 + 1], ssq.y);
+    __syncthreads();
+    for (int i = tid; i < CC * 2; i += nthr) {
+      const int ch = cbase + i / 2;
+      const float v = s_stat[i];
+      if (ch < Cp && v != 0.f) atomicAdd(&stats[((int64_t)n * Cp + ch) * 2 + (i & 1)], (double)v);
+    }
+  }
+}
+
+struct TilePlan {
+  TileGeom g;
+  dim3 grid;
+  int threads, CC, TW, PW, IH, IW;
+  size_t smem;
+  bool ok;
+};
+
+// candidates compiled below
+constexpr int kCC[3] = {48, 56, 72};
+
+template <int MODE>
+constexpr int tw_small() { return (MODE == M_FWD2) ? 4 : 8; }
+template <int MODE>
+constexpr int tw_big() { return (MODE == M_FWD2) ? 8 : 16; }
+
+// (Ho, Wo): extents of the produced tensor
+template <typename T, int MODE>
+TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW) {
+  using M = Map<MODE>;
+  TilePlan p;
+  p.ok = false;
+  p.PW = PW;
+  const int MAX_THREADS = PW == 4 ? 384 : 256;
+  TileGeom& g = p.g;
+  g.T = T_; g.Cp = Cp; g.Ho = Ho; g.Wo = Wo;
+  const int esz = (int)sizeof(T);
+  // Pick (TH, TW, CC) maximising the fraction of useful lanes (ragged tiles, partial channel chunks)
+  // with a mild penalty for halo re-reads and for small CTAs.
+  double best = -1.0;
+  for (int ci = 0; ci < 3; ++ci) {
+    const int CC = kCC[ci];
+    const int nchunk = (Cp + CC - 1) / CC;
+    for (int twi = 0; twi < 2; ++twi) {
+      const int TW = twi ? tw_big<MODE>() : tw_small<MODE>();
+      if (TW % PW) continue;
+      for (int TH = PH; TH <= 8; TH += PH) {
+        const int patches = (TH / PH) * (TW / PW);
+        const int threads = patches * (CC / 2);
+        if (threads < 96 || threads > MAX_THREADS) continue;
+        const int th = (Ho + TH - 1) / TH, tw = (Wo + TW - 1) / TW;
+        const int IH = M::in_ext(TH), IW = M::in_ext(TW);
+        if (IH > 256 || IW > 256) continue;
+        const size_t smem = (size_t)NSTAGE * IH * IW * CC * esz;
+        if (smem > 160 * 1024) continue;
+        const double useful = (double)Ho * Wo * Cp / ((double)th * TH * tw * TW * nchunk * CC);
+        const double in_per_out = MODE == M_FWD2 ? 4.0 : MODE == M_DG2 ? 0.25 : 1.0;
+        const double halo = (double)IH * IW / ((double)TH * TW * in_per_out);
+        const double score = useful / (1.0 + 0.3 * (halo - 1.0)) * (threads >= 192 ? 1.0 : 0.9);
+        if (score > best) {
+          best = score;
+          g.TH = TH; p.TW = TW; p.CC = CC; p.threads = threads;
+        }
+      }
+    }
+  }
+  if (best < 0.45) return p;    // too wasteful (exotic channel counts): let the direct kernel do it
+  g.tiles_w = (Wo + p.TW - 1) / p.TW;
+  const int tiles_h = (Ho + g.TH - 1) / g.TH;
+  p.IH = M::in_ext(g.TH);
+  p.IW = M::in_ext(p.TW);
+  const size_t plane_bytes = (size_t)p.IH * p.IW * p.CC * esz;
+  const size_t stage_bytes = (plane_bytes + 127) / 128 * 128;
+  g.stage_elems = (int)(stage_bytes / esz);
+  p.smem = NSTAGE * stage_bytes + (size_t)p.CC * 2 * sizeof(float) + NSTAGE * sizeof(uint64_t) + 16;
+  p.grid = dim3((unsigned)(g.tiles_w * tiles_h), (unsigned)((Cp + p.CC - 1) / p.CC), (unsigned)N);
+  if (N > 65535 || (int64_t)Ho * Wo * Cp >= (1ll << 31)) return p;
+  p.ok = true;
+  return p;
+}
+
+// ---- tensor map (driver entry point fetched through the runtime: no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NDHWC tensor [N][T_][H][W][Cp] staged in boxes of [IH][IW][CC]
+template <typename T>
+bool make_input_map(CUtensorMap* map, const void* x, int64_t N, int T_, int H, int W, int Cp, int CC, int IW, int IH,
+                    bool nan_fill) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t esz = sizeof(T);
+  cuuint64_t dims[5] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T_, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)Cp * esz, (cuuint64_t)W * Cp * esz, (cuuint64_t)H * W * Cp * esz,
+                           (cuuint64_t)T_ * H * W * Cp * esz};
+  cuuint32_t box[5] = {(cuuint32_t)CC, (cuuint32_t)IW, (cuuint32_t)IH, 1u, 1u};
+  cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  const CUtensorMapDataType dt = sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(map, dt, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+using Args = x3d::DwTiledArgs;
+
+template <typename T, int MODE, int CC, int TW, int PW, bool XF, bool AUX>
+void launch_one(const TilePlan& p, const CUtensorMap& map, const Args& a, cudaStream_t stream) {
+  auto kfn = dw3_tiled_kernel<T, MODE, CC, TW, PW, XF, AUX>;
+  static bool attr_done = false;   // per instantiation
+  if (!attr_done) {
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  kfn<<<p.grid, p.threads, p.smem, stream>>>(map, a.w, (T*)a.y, p.g, a.scale, a.shift, a.splits, (const T*)a.aux,
+                                             a.stats);
+}
+
+template <typename T, int MODE, int PW>
+int launch_tiled(const TilePlan& p, const CUtensorMap& map, const Args& a, cudaStream_t stream) {
+  constexpr bool DG = MODE >= 2;
+  constexpr int TWa = tw_small<MODE>(), TWb = tw_big<MODE>();
+  const bool flag = DG ? (a.aux != nullptr) : (a.scale != nullptr);
+#define L2_(CCv, TWv)                                                               \
+  do {                                                                              \
+    if (flag) launch_one<T, MODE, CCv, TWv, PW, !DG, DG>(p, map, a, stream);        \
+    else launch_one<T, MODE, CCv, TWv, PW, false, false>(p, map, a, stream);        \
+  } while (0)
+#define L_(CCv)                                    \
+  if (p.CC == CCv) {                               \
+    if (p.TW == TWa) L2_(CCv, TWa);                \
+    else L2_(CCv, TWb);                            \
+    return 0;                                      \
+  }
+  L_(48) L_(56) L_(72)
+#undef L_
+#undef L2_
+  return -1;
+}
+
+// in: staged tensor [N][T_][Hin][Win][Cp]; produced tensor has extents (Ho, Wo)
+template <typename T, int MODE>
+int run_tiled(const void* in, int64_t N, int T_, int Hin, int Win, int Ho, int Wo, int Cp, const Args& a,
+              cudaStream_t stream, int PW, bool nan_fill, bool* handled) {
+  TilePlan p = plan_tiles<T, MODE>(N, T_, Ho, Wo, Cp, PW);
+  if (!p.ok) return 0;
+  CUtensorMap map;
+  if (!make_input_map<T>(&map, in, N, T_, Hin, Win, Cp, p.CC, p.IW, p.IH, nan_fill)) return 0;
+  const int rc = launch_tiled<T, MODE, 2>(p, map, a, stream);   // PW = 4 (1 CTA/SM) measured slower
+  if (rc != 0) return 0;
+  *handled = true;
+  return 0;
+}
+
+}  // namespace
+
+namespace x3d {
+// one translation unit per storage type (DW_T): halves the build time of the 48 kernel instantiations
+int DW_TILED_ENTRY(int mode, const void* in, int64_t N, int T_, int Hin, int Win, int Ho, int Wo, int Cp,
+                   const DwTiledArgs& a, cudaStream_t stream, bool nan_fill, bool* handled) {
+  const int PW = 2;
+  switch (mode) {
+    case M_FWD1: return run_tiled<DW_T, M_FWD1>(in, N, T_, Hin, Win, Ho, Wo, Cp, a, stream, PW, nan_fill, handled);
+    case M_FWD2: return run_tiled<DW_T, M_FWD2>(in, N, T_, Hin, Win, Ho, Wo, Cp, a, stream, PW, nan_fill, handled);
+    case M_DG1: return run_tiled<DW_T, M_DG1>(in, N, T_, Hin, Win, Ho, Wo, Cp, a, stream, PW, nan_fill, handled);
+    default: return run_tiled<DW_T, M_DG2>(in, N, T_, Hin, Win, Ho, Wo, Cp, a, stream, PW, nan_fill, handled);
+  }
+}
+}  // namespace x3d

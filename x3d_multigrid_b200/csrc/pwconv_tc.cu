@@ -1,9 +1,382 @@
-// tcgen05 / TMEM / TMA pointwise-conv GEMM (bf16).  Placeholder: not yet enabled.
+// Pointwise (1x1x1) Conv3d forward / dgrad as a tcgen05 GEMM (bf16 in, fp32 accumulate in TMEM).
+//
+//   C[m][n] = sum_k A[m][k] * B[n][k]      A: activations [M][Kp] (NDHWC rows), B: weights [Np][Kp]
+//
+// One CTA per 128 x BN output tile (BN = whole N up to 256, else N split in equal parts), 6 warps:
+//   warp 0  : TMA producer  -- per 64-wide K chunk one box of A (128 x 64) and one of B (BN x 64) into a
+//             4-stage shared-memory ring (SWIZZLE_128B), completion on "full" mbarriers;
+//   warp 1  : allocates TMEM, then one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//             (M=128, N=BN, K=16) per 16-wide K step, tcgen05.commit frees the ring slot ("empty") and
+//             finally signals the accumulator ("accum") to the epilogue;
+//   warps 2-5: epilogue -- tcgen05.ld of their 32 TMEM lanes (= 32 output rows), bf16 pack, 16-byte
+//             global stores, and (forward) the per-sample column sums / sums of squares that feed the
+//             following SubBatchNorm3d: a 5-step butterfly transpose-reduce across the warp (1 shuffle
+//             per column instead of 5), shared-memory merge of the 4 warps, one fp64 atomic per column.
+// K and N of this network are small (24..432) and M is huge: every layer is HBM-bound,
+// so the design goal is simply to stream A and C at full bandwidth with several CTAs in flight per SM.
+#include <cuda.h>
+
 #include "common.cuh"
+
+using namespace x3d;
+
+namespace {
+
+constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int NTHREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);          // start address
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                            // layout: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format  = F32
+  d |= 1u << 7;                       // a_format  = BF16
+  d |= 1u << 10;                      // b_format  = BF16
+  d |= (uint32_t)(n >> 3) << 17;      // n_dim
+  d |= (uint32_t)(BM >> 4) << 24;     // m_dim
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+struct TcParams {
+  int M, Kp, Np, BN, nk, tmem_cols, ldc;
+  long long P_out;
+};
+
+// 16 values per lane (row = lane) -> each lane ends with the sum over the 32 rows of column
+// ((lane>>1) & 15); 16 shuffles instead of 80.
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float send = up ? v[j] : v[j + 8];
+      const float keep = up ? v[j + 8] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float send = up ? v[j] : v[j + 4];
+      const float keep = up ? v[j + 4] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float send = up ? v[j] : v[j + 2];
+      const float keep = up ? v[j + 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+// column (0..15) whose total a lane holds after butterfly16
+__device__ __forceinline__ int butterfly_col(int lane) {
+  return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(NTHREADS)
+pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+             __nv_bfloat16* __restrict__ C, const TcParams p, double* __restrict__ stats) {
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte aligned operand ring (SWIZZLE_128B atoms)
+  const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
+  const int BN = p.BN;
+  const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)BN * BK * 2;
+  unsigned char* a_s = base;
+  unsigned char* b_s = base + STAGES * a_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(b_s + STAGES * b_bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);      // [2 samples][BN][2]
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;           // BN-sized column parts start at multiples of the part width
+  const int ncols = (p.Np - n0 < BN) ? p.Np - n0 : BN;          // valid columns of this tile
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapB) : "memory");
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (STATS && warp >= 2) {
+    for (int i = threadIdx.x - 64; i < 2 * BN * 2; i += NTHREADS - 64) s_stat[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kc = 0; kc < p.nk; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+        tma_load_2d(a_s + s * a_bytes, &mapA, &full_bar[s], kc * BK, m0);
+        tma_load_2d(b_s + s * b_bytes, &mapB, &full_bar[s], kc * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      for (int kc = 0; kc < p.nk; ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const int krem = p.Kp - kc * BK;
+        const int ksteps = krem >= BK ? BK / 16 : (krem + 15) / 16;
+        const uint32_t a_addr = smem_u32(a_s + s * a_bytes), b_addr = smem_u32(b_s + s * b_bytes);
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t adesc = make_smem_desc(a_addr + k * 32);
+          const uint64_t bdesc = make_smem_desc(b_addr + k * 32);
+          umma_f16(tmem_base, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);          // ring slot reusable once these MMAs have read it
+      }
+      umma_commit(accum_bar);                // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;                                // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    __nv_bfloat16* crow = C + (int64_t)row * p.ldc + n0;
+    long long samp = 0;
+    int slot = 0;
+    bool uniform = true;
+    if (STATS) {
+      const long long first = (long long)m0 / p.P_out;
+      samp = (long long)(row_ok ? row : m0) / p.P_out;
+      const long long s0 = __shfl_sync(0xffffffffu, samp, 0);
+      uniform = __all_sync(0xffffffffu, samp == s0 || !row_ok);
+      slot = (int)(s0 - first);
+      if (slot > 1) uniform = false;
+    }
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr + c0, r);
+      if (c0 >= ncols) continue;                           // (warp-uniform) padding columns of the MMA
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+      if (row_ok) {
+        if (c0 + 8 <= ncols) *reinterpret_cast<uint4*>(crow + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (c0 + 16 <= ncols) *reinterpret_cast<uint4*>(crow + c0 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      if (STATS) {
+        float v[16], v2[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[2 * j] = row_ok ? __uint_as_float(w[j] << 16) : 0.f;
+          v[2 * j + 1] = row_ok ? __uint_as_float(w[j] & 0xffff0000u) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v2[j] = v[j] * v[j];
+        if (uniform) {
+          const float s1 = butterfly16(v, lane);
+          const float s2 = butterfly16(v2, lane);
+          const int col = c0 + butterfly_col(lane);
+          if ((lane & 1) == 0 && col < ncols) {
+            atomicAdd(&s_stat[(slot * BN + col) * 2 + 0], s1);
+            atomicAdd(&s_stat[(slot * BN + col) * 2 + 1], s2);
+          }
+        } else if (row_ok) {
+          // tile straddles more than two samples (tiny feature maps): rare, per-element fp64 atomics
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (c0 + j < ncols) {
+              double* gp = stats + (samp * p.ldc + n0 + c0 + j) * 2;
+              atomicAdd(gp, (double)v[j]);
+              atomicAdd(gp + 1, (double)v2[j]);
+            }
+          }
+        }
+      }
+    }
+    if (STATS) {
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");     // the four epilogue warps
+      const long long first = (long long)m0 / p.P_out;
+      for (int i = threadIdx.x - 64; i < 2 * BN * 2; i += 128) {
+        const int sl = i / (BN * 2), rem = i % (BN * 2), col = rem >> 1;
+        const float v = s_stat[i];
+        if (col < ncols && v != 0.f)
+          atomicAdd(&stats[((first + sl) * p.ldc + n0 + col) * 2 + (rem & 1)], (double)v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// row-major bf16 matrix [rows][cols]; boxes of [box_rows][64] with 128-byte swizzle
+bool make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
 namespace x3d {
-int pwconv_fwd_tc(const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t, double*, cudaStream_t,
-                  bool* handled) {
+// y[M][Np] = x[M][Kp] * w[Np][Kp]^T  (all bf16, dense rows).  *handled = false -> caller uses the SIMT path.
+int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, int64_t Np, int64_t P_out,
+                  double* stats, cudaStream_t stream, bool* handled) {
   *handled = false;
+  static const bool off = getenv("X3D_PW_SIMT") != nullptr;      // A/B switch for tests and profiling
+  if (off) return 0;
+  if (M < 1 || Kp % 8 || Np % 8 || M >= (1ll << 31)) return 0;
+  // column tiles of width BN (multiple of 16, <= 256): the whole N when it fits one MMA, else N split in
+  // near-equal parts; tile j covers columns [j*BN, min((j+1)*BN, Np)), weight rows beyond Np are TMA zero fill
+  const int parts = (int)((Np + 255) / 256);
+  const int BN = (int)(((Np + parts - 1) / parts + 15) / 16 * 16);
+  if (BN > 256) return 0;
+  TcParams p;
+  p.M = (int)M; p.Kp = (int)Kp; p.Np = (int)Np; p.BN = BN; p.ldc = (int)Np;
+  p.nk = (int)((Kp + BK - 1) / BK);
+  p.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  p.P_out = P_out;
+  CUtensorMap mapA, mapB;
+  if (!make_map_2d(&mapA, x, M, Kp, BM)) return 0;
+  if (!make_map_2d(&mapB, w, Np, Kp, BN)) return 0;
+  const size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + (size_t)BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 +
+                      (stats ? (size_t)2 * BN * 2 * sizeof(float) : 0);
+  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((Np + BN - 1) / BN));
+  static bool attr_done[2] = {false, false};
+  if (stats) {
+    if (!attr_done[1]) { cudaFuncSetAttribute(pw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done[1] = true; }
+    pw_tc_kernel<true><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, (__nv_bfloat16*)y, p, stats);
+  } else {
+    if (!attr_done[0]) { cudaFuncSetAttribute(pw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done[0] = true; }
+    pw_tc_kernel<false><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, (__nv_bfloat16*)y, p, nullptr);
+  }
+  *handled = true;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("pwconv_fwd_tc: launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  count_launch();
   return 0;
 }
 }  // namespace x3d
