@@ -16,6 +16,9 @@ int dwconv_dgrad_tiled(const void* dy, const float* w_packed, void* dx, int64_t 
                        int64_t Cp, int stride, const void* mask_src, const float* mask_scale,
                        const float* mask_shift, int splits, double* stats, x3d_dtype_t dt, cudaStream_t stream,
                        bool* handled);
+int dwconv_wgrad_tiled(const void* x, const void* dy, float* dw, int64_t N, int64_t T, int64_t H, int64_t W,
+                       int64_t C, int64_t Cp, int stride, const float* in_scale, const float* in_shift, int splits,
+                       int relu_in, x3d_dtype_t dt, cudaStream_t stream, bool* handled);
 }
 
 struct DwGeom {
@@ -355,6 +358,12 @@ extern "C" int x3d_dwconv_wgrad(const void* x, const void* dy, float* dw, int64_
   g.Wo = (int)((W + 2 * (kw / 2) - kw) / stride + 1);
   const int64_t P = T_ * g.Ho * g.Wo;
   if (N * P == 0) return 0;
+  if (kt == 3) {
+    bool handled = false;
+    int rc = dwconv_wgrad_tiled(x, dy, dw, N, T_, H, W, C, Cp, stride, in_scale, in_shift, splits, relu_in, dt,
+                                as_stream(stream), &handled);
+    if (handled) return rc;
+  }
 #define L_(KT_, KH_, KW_, XF, RL)                                                                               \
   dw_wgrad_direct_kernel<T, KT_, KH_, KW_, XF, RL><<<grid, rg.threads, smem, as_stream(stream)>>>(              \
       (const T*)x, (const T*)dy, dw, g, (int)C, in_scale, in_shift, splits, P, rg.cv, rg.rows, rg.chunk)

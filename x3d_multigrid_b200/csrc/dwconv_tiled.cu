@@ -57,4 +57,21 @@ int dwconv_dgrad_tiled(const void* dy, const float* w_packed, void* dx, int64_t 
     dw_tiled_run_f32(mode, dy, N, (int)T_, Ho, Wo, (int)H, (int)W, (int)Cp, a, stream, false, handled);
   return finish("dwconv_dgrad_tiled", *handled);
 }
+
+// dw[C][27] += wgrad(x (conv input, optional fused BN+ReLU), dy)
+int dwconv_wgrad_tiled(const void* x, const void* dy, float* dw, int64_t N, int64_t T_, int64_t H, int64_t W,
+                       int64_t C, int64_t Cp, int stride, const float* in_scale, const float* in_shift, int splits,
+                       int relu_in, x3d_dtype_t dt, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  if (force_direct()) return 0;
+  if (in_scale != nullptr && !relu_in) return 0;
+  const int Ho = (int)((H + 2 - 3) / stride + 1), Wo = (int)((W + 2 - 3) / stride + 1);
+  if (dt == X3D_BF16)
+    dw_wgrad_tiled_bf16(stride, x, dy, dw, N, (int)T_, (int)H, (int)W, Ho, Wo, (int)C, (int)Cp, in_scale, in_shift,
+                        splits, stream, handled);
+  else
+    dw_wgrad_tiled_f32(stride, x, dy, dw, N, (int)T_, (int)H, (int)W, Ho, Wo, (int)C, (int)Cp, in_scale, in_shift,
+                       splits, stream, handled);
+  return finish("dwconv_wgrad_tiled", *handled);
+}
 }  // namespace x3d

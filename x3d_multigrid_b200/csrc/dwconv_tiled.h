@@ -17,4 +17,10 @@ int dw_tiled_run_bf16(int mode, const void* in, int64_t N, int T_, int Hin, int 
                       const DwTiledArgs& a, cudaStream_t stream, bool nan_fill, bool* handled);
 int dw_tiled_run_f32(int mode, const void* in, int64_t N, int T_, int Hin, int Win, int Ho, int Wo, int Cp,
                      const DwTiledArgs& a, cudaStream_t stream, bool nan_fill, bool* handled);
+int dw_wgrad_tiled_bf16(int stride, const void* x, const void* dy, float* dw, int64_t N, int T_, int H, int W, int Ho,
+                        int Wo, int C, int Cp, const float* scale, const float* shift, int splits,
+                        cudaStream_t stream, bool* handled);
+int dw_wgrad_tiled_f32(int stride, const void* x, const void* dy, float* dw, int64_t N, int T_, int H, int W, int Ho,
+                       int Wo, int C, int Cp, const float* scale, const float* shift, int splits,
+                       cudaStream_t stream, bool* handled);
 }  // namespace x3d

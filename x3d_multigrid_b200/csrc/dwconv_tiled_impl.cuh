@@ -507,9 +507,225 @@ int run_tiled(const void* in, int64_t N, int T_, int Hin, int Win, int Ho, int W
   return 0;
 }
 
+// =================================================================================================
+// wgrad:  dW[c][kt][kh][kw] += sum_{n,t,ho,wo} dy[n,t,ho,wo,c] * xf[n, t+kt-1, s*ho+kh-1, s*wo+kw-1, c]
+// Same CTA / thread decomposition as the forward kernel.  Per T step the ring delivers the input-plane
+// tile x[tin] (with halo, BN+ReLU fused on load, NaN -> 0 padding) and the dy tile of plane tin+1; a
+// thread keeps its dy patch of planes tin+1 / tin / tin-1 in registers (they rotate like the forward
+// accumulators) and its 27 x 2 weight-gradient accumulators: every window word feeds up to 27 FFMA2.
+// Reduction: shared atomics across the patches of the CTA, then one fp32 red per (channel, tap) per CTA.
+// =================================================================================================
+template <typename T, int MODE, int CC, int TW, int PW, bool XF>
+__global__ void __launch_bounds__(Cfg<PW>::MAXT, Cfg<PW>::MINB)
+dw3_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap dymap,
+                       float* __restrict__ dw, const TileGeom g, const float* __restrict__ scale,
+                       const float* __restrict__ shift, int splits, int C, int dy_stage_elems) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using M = Map<MODE>;                                           // forward geometry (MODE = M_FWD1 / M_FWD2)
+  constexpr int WR = M::in_ext(PH), WC = M::in_ext(PW);
+  constexpr int IW = M::in_ext(TW);
+  constexpr int ROW = IW * CC;
+  constexpr int PAIRS = CC / 2;
+  constexpr int PPR = TW / PW;
+  constexpr int NO = PH * PW;
+  const int IH = M::in_ext(g.TH);
+  const int Cp = g.Cp;
+  T* const xbuf = reinterpret_cast<T*>(smem_raw);                            // NSTAGE x tiles
+  T* const dbuf = xbuf + NSTAGE * g.stage_elems;                              // NSTAGE dy tiles
+  float* s_red = reinterpret_cast<float*>(dbuf + NSTAGE * dy_stage_elems);    // [27][CC]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_red + 27 * CC);
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int ho0 = (blockIdx.x / g.tiles_w) * g.TH, wo0 = (blockIdx.x % g.tiles_w) * TW;
+  const int cbase = blockIdx.y * CC;
+  const int n = blockIdx.z;
+  const int pair = tid % PAIRS, patch = tid / PAIRS;
+  const int py = patch / PPR, px = patch % PPR;
+  const int c = cbase + 2 * pair;
+  const bool ch_ok = c < Cp;
+  const int hi0 = M::in_org(ho0), wi0 = M::in_org(wo0);
+  const int nT = g.T;
+  const uint32_t x_bytes = (uint32_t)(IH * ROW * sizeof(T));
+  const uint32_t dy_bytes = (uint32_t)(g.TH * TW * CC * sizeof(T));
+
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < NSTAGE; ++k) mbar_init(&full_bar[k], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  for (int i = tid; i < 27 * CC; i += nthr) s_red[i] = 0.f;
+  __syncthreads();
+  // step s (s = -1 .. T-1) needs x[s] (if s >= 0) and dy[s+1] (if s+1 < T)
+  auto issue = [&](int s, int slot) {
+    const bool hx = s >= 0, hd = s + 1 < nT;
+    mbar_expect_tx(&full_bar[slot], (hx ? x_bytes : 0u) + (hd ? dy_bytes : 0u));
+    if (hx) tma_load_5d(xbuf + slot * g.stage_elems, &xmap, &full_bar[slot], cbase, wi0, hi0, s, n);
+    if (hd) tma_load_5d(dbuf + slot * dy_stage_elems, &dymap, &full_bar[slot], cbase, wo0, ho0, s + 1, n);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < NSTAGE - 1; ++k)
+      if (k - 1 < nT) issue(k - 1, k);
+  }
+
+  float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+  if (XF && ch_ok) {
+    const int b = n % splits;
+    sc = *reinterpret_cast<const float2*>(scale + (int64_t)b * Cp + c);
+    sh = *reinterpret_cast<const float2*>(shift + (int64_t)b * Cp + c);
+  }
+  const int win_base = (M::win_off(py * PH) * IW + M::win_off(px * PW)) * CC + 2 * pair;
+  const int dy_base = ((py * PH) * TW + px * PW) * CC + 2 * pair;
+
+  float2 gacc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) gacc[k] = make_float2(0.f, 0.f);
+  float2 dyA[NO], dyB[NO], dyC[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) dyA[o] = dyB[o] = dyC[o] = make_float2(0.f, 0.f);
+
+  int slot = 0;
+  uint32_t parity = 0;
+  // step s: `nw` receives dy plane s+1; with x plane s:  kt=0 pairs with nw (plane s+1), kt=1 with md
+  // (plane s), kt=2 with od (plane s-1)
+  auto step = [&](int s, float2 (&nw)[NO], const float2 (&md)[NO], const float2 (&od)[NO]) {
+    mbar_wait(&full_bar[slot], parity);
+    __syncthreads();
+    if (tid == 0) {
+      const int sn_step = s + NSTAGE - 1;
+      int sn = slot + NSTAGE - 1;
+      if (sn >= NSTAGE) sn -= NSTAGE;
+      if (sn_step < nT) issue(sn_step, sn);
+    }
+    const T* bp = xbuf + slot * g.stage_elems + win_base;
+    const T* dp = dbuf + slot * dy_stage_elems + dy_base;
+    if (++slot == NSTAGE) { slot = 0; parity ^= 1u; }
+    if (s + 1 < nT) {
+#pragma unroll
+      for (int oy = 0; oy < PH; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < PW; ++ox) nw[oy * PW + ox] = lds_pair<T>(dp + (oy * TW + ox) * CC);
+    } else {
+#pragma unroll
+      for (int o = 0; o < NO; ++o) nw[o] = make_float2(0.f, 0.f);
+    }
+    if (s < 0) return;
+#pragma unroll
+    for (int r = 0; r < WR; ++r) {
+#pragma unroll
+      for (int cc = 0; cc < WC; ++cc) {
+        float2 xv = lds_pair<T>(bp + r * ROW + cc * CC);
+        if (XF) {
+          xv = __ffma2_rn(xv, sc, sh);
+          xv.x = fmaxf(xv.x, 0.f);
+          xv.y = fmaxf(xv.y, 0.f);
+        }
+#pragma unroll
+        for (int oy = 0; oy < PH; ++oy) {
+          const int kh = M::tap(r, oy);
+          if (kh < 0 || kh > 2) continue;
+#pragma unroll
+          for (int ox = 0; ox < PW; ++ox) {
+            const int kw = M::tap(cc, ox);
+            if (kw < 0 || kw > 2) continue;
+            const int o = oy * PW + ox, tap = kh * 3 + kw;
+            gacc[tap] = __ffma2_rn(nw[o], xv, gacc[tap]);
+            gacc[9 + tap] = __ffma2_rn(md[o], xv, gacc[9 + tap]);
+            gacc[18 + tap] = __ffma2_rn(od[o], xv, gacc[18 + tap]);
+          }
+        }
+      }
+    }
+  };
+
+  // steps -1, 0, ..., T-1 with the dy register sets rotating (A,B,C) -> (C,A,B) -> (B,C,A)
+  int s = -1;
+  for (; s + 3 <= nT; s += 3) {
+    step(s, dyA, dyB, dyC);
+    step(s + 1, dyC, dyA, dyB);
+    step(s + 2, dyB, dyC, dyA);
+  }
+  if (s < nT) {
+    step(s, dyA, dyB, dyC);
+    if (s + 1 < nT) step(s + 1, dyC, dyA, dyB);
+  }
+
+  // ---- reduction: patches of the CTA -> shared, CTA -> global ------------------------------------
+  if (ch_ok) {
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      atomicAdd(&s_red[k * CC + 2 * pair], gacc[k].x);
+      atomicAdd(&s_red[k * CC + 2 * pair + 1], gacc[k].y);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 27 * CC; i += nthr) {
+    const int k = i / CC, ch = cbase + i % CC;
+    const float v = s_red[i];
+    if (ch < C && v != 0.f) atomicAdd(&dw[(int64_t)ch * 27 + k], v);
+  }
+}
+
+template <typename T, int MODE, int CC, int TW, bool XF>
+void launch_wgrad_one(const TilePlan& p, const CUtensorMap& xmap, const CUtensorMap& dymap, float* dw,
+                      const float* scale, const float* shift, int splits, int C, int dy_stage_elems, size_t smem,
+                      cudaStream_t stream) {
+  auto kfn = dw3_wgrad_tiled_kernel<T, MODE, CC, TW, 2, XF>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  kfn<<<p.grid, p.threads, smem, stream>>>(xmap, dymap, dw, p.g, scale, shift, splits, C, dy_stage_elems);
+}
+
+// x: [N][T_][H][W][Cp] (conv input), dy: [N][T_][Ho][Wo][Cp]
+template <typename T, int MODE>
+int run_wgrad_tiled(const void* x, const void* dy, float* dw, int64_t N, int T_, int H, int W, int Ho, int Wo, int C,
+                    int Cp, const float* scale, const float* shift, int splits, cudaStream_t stream, bool* handled) {
+  TilePlan p = plan_tiles<T, MODE>(N, T_, Ho, Wo, Cp, 2);
+  if (!p.ok) return 0;
+  const size_t esz = sizeof(T);
+  const size_t dy_stage_bytes = ((size_t)p.g.TH * p.TW * p.CC * esz + 127) / 128 * 128;
+  const size_t smem = NSTAGE * ((size_t)p.g.stage_elems * esz + dy_stage_bytes) + (size_t)27 * p.CC * sizeof(float) +
+                      NSTAGE * sizeof(uint64_t) + 16;
+  if (smem > 200 * 1024) return 0;
+  CUtensorMap xmap, dymap;
+  if (!make_input_map<T>(&xmap, x, N, T_, H, W, Cp, p.CC, p.IW, p.IH, scale != nullptr)) return 0;
+  if (!make_input_map<T>(&dymap, dy, N, T_, Ho, Wo, Cp, p.CC, p.TW, p.g.TH, false)) return 0;
+  constexpr int TWa = tw_small<MODE>(), TWb = tw_big<MODE>();
+  const bool xf = scale != nullptr;
+  const int dse = (int)(dy_stage_bytes / esz);
+#define W2_(CCv, TWv)                                                                                             \
+  do {                                                                                                            \
+    if (xf) launch_wgrad_one<T, MODE, CCv, TWv, true>(p, xmap, dymap, dw, scale, shift, splits, C, dse, smem, stream);   \
+    else launch_wgrad_one<T, MODE, CCv, TWv, false>(p, xmap, dymap, dw, scale, shift, splits, C, dse, smem, stream);    \
+  } while (0)
+#define W_(CCv)                                    \
+  if (p.CC == CCv) {                               \
+    if (p.TW == TWa) W2_(CCv, TWa);                \
+    else W2_(CCv, TWb);                            \
+    *handled = true;                               \
+    return 0;                                      \
+  }
+  W_(48) W_(56) W_(72)
+#undef W_
+#undef W2_
+  return 0;
+}
+
 }  // namespace
 
 namespace x3d {
+int DW_WGRAD_ENTRY(int stride, const void* x, const void* dy, float* dw, int64_t N, int T_, int H, int W, int Ho,
+                   int Wo, int C, int Cp, const float* scale, const float* shift, int splits, cudaStream_t stream,
+                   bool* handled) {
+  if (stride == 1)
+    return run_wgrad_tiled<DW_T, M_FWD1>(x, dy, dw, N, T_, H, W, Ho, Wo, C, Cp, scale, shift, splits, stream, handled);
+  return run_wgrad_tiled<DW_T, M_FWD2>(x, dy, dw, N, T_, H, W, Ho, Wo, C, Cp, scale, shift, splits, stream, handled);
+}
+
 // one translation unit per storage type (DW_T): halves the build time of the 48 kernel instantiations
 int DW_TILED_ENTRY(int mode, const void* in, int64_t N, int T_, int Hin, int Win, int Ho, int Wo, int Cp,
                    const DwTiledArgs& a, cudaStream_t stream, bool nan_fill, bool* handled) {

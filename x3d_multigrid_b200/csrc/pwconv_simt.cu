@@ -11,6 +11,8 @@ using namespace x3d;
 namespace x3d {
 int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, int64_t Np, int64_t P_out,
                   double* stats, cudaStream_t stream, bool* handled);
+int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t K, int64_t Kp, int64_t Nn,
+                    int64_t Np, cudaStream_t stream, bool* handled);
 }
 
 struct RowMap {
@@ -292,6 +294,11 @@ extern "C" int x3d_pwconv_wgrad(const void* x, const void* dy, float* dw, int64_
   RowMap map = make_map(T_, H, W, stride);
   const int64_t M = N * T_ * map.Ho * map.Wo;
   if (M == 0) return 0;
+  if (dt == X3D_BF16 && stride == 1) {
+    bool handled = false;
+    int rc = pwconv_wgrad_tc(x, dy, dw, M, K, Kp, Nn, Np, as_stream(stream), &handled);
+    if (handled) return rc;
+  }
   const int nt = (int)cdiv(Nn, 64), kt = (int)cdiv(K, 64);
   int64_t splits = cdiv(4 * kNumSMs, (int64_t)nt * kt);
   int64_t max_splits = cdiv(M, 4 * WM);

@@ -336,9 +336,198 @@ bool make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// =================================================================================================
+// wgrad:  dW[n][k] += sum_m dY[m][n] * X[m][k]
+// Both operands have the reduction index m as their SLOW memory index, i.e. they are "MN-major" UMMA
+// operands: a TMA box of 64 rows (m) x 64 columns gives exactly the canonical SWIZZLE_128B MN-major
+// atom layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: SBO = 1024 B between 8-row groups,
+// LBO = 8192 B between 64-column blocks.  A = dY^T (M' = 128 columns n per CTA), B = X^T (N' <= 256
+// columns k), D[n][k] accumulates in TMEM over the CTA's chunk of rows, then fp32 red.global.add into dW.
+// =================================================================================================
+constexpr int WG_ROWS = 64;                       // m rows per ring stage (4 MMAs of K = 16)
+constexpr int WG_STAGES = 3;
+constexpr int WG_BOX_BYTES = WG_ROWS * 128;       // one 64 x 64 bf16 box
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;          // LBO: next 64-column block
+  d |= (uint64_t)(1024 >> 4) << 32;                  // SBO: next group of 8 rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_mn(int n) {
+  return make_idesc(n) | (1u << 15) | (1u << 16);    // A and B are MN-major
+}
+
+struct WgParams {
+  int M, K, Kp, Nn, Np;
+  int NB;            // MMA N (columns k handled by this CTA's part), multiple of 16
+  int a_boxes, b_boxes_full;   // 64-wide boxes per stage for A (1 or 2 valid) and for a full B part
+  int rows_per_cta;
+  int tmem_cols;
+};
+
+__global__ void __launch_bounds__(NTHREADS)
+pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
+                   float* __restrict__ dW, const WgParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
+  constexpr int A_BYTES = 2 * WG_BOX_BYTES;                   // 128 columns n
+  const int b_stage_bytes = 4 * WG_BOX_BYTES;                 // up to 256 columns k
+  const int stage_bytes = A_BYTES + b_stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + WG_STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + WG_STAGES;
+  uint64_t* accum_bar = empty_bar + WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n0 = blockIdx.y * 128;
+  const int k0 = blockIdx.z * p.NB;
+  const int64_t row0 = (int64_t)blockIdx.x * p.rows_per_cta;
+  int64_t row1 = row0 + p.rows_per_cta;
+  if (row1 > p.M) row1 = p.M;
+  const int nsteps = (int)((row1 - row0 + WG_ROWS - 1) / WG_ROWS);
+  // boxes actually worth loading (the rest of the MMA operand is don't-care: those D rows/cols are never stored)
+  const int a_boxes = (p.Np - n0 > 64) ? 2 : 1;
+  int b_boxes = (p.Kp - k0 + 63) / 64;
+  const int b_need = (p.NB + 63) / 64;
+  if (b_boxes > b_need) b_boxes = b_need;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapDY) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapX) : "memory");
+#pragma unroll
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < nsteps; ++it) {
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (it / WG_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], (uint32_t)((a_boxes + b_boxes) * WG_BOX_BYTES));
+        unsigned char* st = base + s * stage_bytes;
+        const int m = (int)(row0 + (int64_t)it * WG_ROWS);
+        for (int j = 0; j < a_boxes; ++j) tma_load_2d(st + j * WG_BOX_BYTES, &mapDY, &full_bar[s], n0 + 64 * j, m);
+        for (int j = 0; j < b_boxes; ++j)
+          tma_load_2d(st + A_BYTES + j * WG_BOX_BYTES, &mapX, &full_bar[s], k0 + 64 * j, m);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(p.NB);
+      for (int it = 0; it < nsteps; ++it) {
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (it / WG_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(base + s * stage_bytes), b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int j = 0; j < WG_ROWS / 16; ++j) {
+          // 16 rows of m = two 8-row groups = 2048 bytes further into every 64-column block
+          umma_f16(tmem_base, make_smem_desc_mn(a_addr + j * 2048), make_smem_desc_mn(b_addr + j * 2048), idesc,
+                   (it | j) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int n = n0 + q * 32 + lane;
+    const bool n_ok = n < p.Nn;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* wrow = dW + (int64_t)n * p.K;
+    for (int c0 = 0; c0 < p.NB; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr + c0, r);
+      if (n_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = k0 + c0 + j;
+          const float v = __uint_as_float(r[j]);
+          if (k < p.K && v != 0.f) atomicAdd(wrow + k, v);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 }  // namespace
 
 namespace x3d {
+// dw[Nn][K] (fp32, += ) from x[M][Kp], dy[M][Np] (bf16, dense rows).  *handled = false -> SIMT path.
+int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t K, int64_t Kp, int64_t Nn,
+                    int64_t Np, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  static const bool off = getenv("X3D_PW_SIMT") != nullptr;
+  if (off) return 0;
+  if (M < 1 || Kp % 8 || Np % 8 || M >= (1ll << 31)) return 0;
+  WgParams p;
+  p.M = (int)M; p.K = (int)K; p.Kp = (int)Kp; p.Nn = (int)Nn; p.Np = (int)Np;
+  const int kparts = (int)((Kp + 255) / 256);
+  p.NB = (int)(((Kp + kparts - 1) / kparts + 15) / 16 * 16);
+  if (p.NB > 256) return 0;
+  p.tmem_cols = p.NB <= 32 ? 32 : p.NB <= 64 ? 64 : p.NB <= 128 ? 128 : 256;
+  p.a_boxes = 2; p.b_boxes_full = (p.NB + 63) / 64;
+  const int ntiles = (int)((Np + 127) / 128);
+  const int kz = (int)((Kp + p.NB - 1) / p.NB);
+  int64_t msplit = (2 * kNumSMs + ntiles * kz - 1) / (ntiles * kz);
+  const int64_t max_split = (M + 511) / 512;
+  if (msplit > max_split) msplit = max_split;
+  if (msplit < 1) msplit = 1;
+  int64_t rpc = ((M + msplit - 1) / msplit + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+  msplit = (M + rpc - 1) / rpc;
+  p.rows_per_cta = (int)rpc;
+  CUtensorMap mapDY, mapX;
+  if (!make_map_2d(&mapDY, dy, M, Np, WG_ROWS)) return 0;
+  if (!make_map_2d(&mapX, x, M, Kp, WG_ROWS)) return 0;
+  const size_t smem = 1024 + (size_t)WG_STAGES * 6 * WG_BOX_BYTES + (2 * WG_STAGES + 1) * 8 + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_done = true;
+  }
+  dim3 grid((unsigned)msplit, (unsigned)ntiles, (unsigned)kz);
+  pw_wgrad_tc_kernel<<<grid, NTHREADS, smem, stream>>>(mapDY, mapX, dw, p);
+  *handled = true;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("pwconv_wgrad_tc: launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  count_launch();
+  return 0;
+}
+
 // y[M][Np] = x[M][Kp] * w[Np][Kp]^T  (all bf16, dense rows).  *handled = false -> caller uses the SIMT path.
 int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, int64_t Np, int64_t P_out,
                   double* stats, cudaStream_t stream, bool* handled) {
