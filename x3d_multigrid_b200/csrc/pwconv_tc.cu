@@ -100,6 +100,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 struct TcParams {
   int M, Kp, Np, BN, nk, tmem_cols, ldc;
+  int tiles_m;       // number of 128-row tiles (CTAs stride over them)
+  int stages;        // operand ring depth
+  int cpitch;        // staging row pitch in elements (BN + 8: conflict-free 16-byte st.shared)
+  int cpa;           // 1: A tile copied by cp.async (narrow rows), 0: by TMA
+  int dbg;           // profiling experiments (X3D_TC_DBG): 1 = skip copy-out, 2 = skip statistics, 4 = skip staging
   long long P_out;
 };
 
@@ -146,38 +151,50 @@ __device__ __forceinline__ int butterfly_col(int lane) {
   return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
 }
 
+// Persistent kernel: grid = (min(tiles_m, resident CTAs), column parts).  Each CTA walks its 128-row tiles;
+// the three roles run as independent pipelines connected by mbarriers:
+//   full/empty[stage]      TMA producer  <-> MMA issuer      (operand ring)
+//   accum_full/empty[buf]  MMA issuer    <-> epilogue warps  (two TMEM accumulators: tile i+1 is being
+//                                                              multiplied while tile i is drained)
 template <bool STATS>
 __global__ void __launch_bounds__(NTHREADS)
 pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-             __nv_bfloat16* __restrict__ C, const TcParams p, double* __restrict__ stats) {
+             const __nv_bfloat16* __restrict__ A, __nv_bfloat16* __restrict__ C, const TcParams p,
+             double* __restrict__ stats) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms)
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
-  const int BN = p.BN;
+  const int BN = p.BN, S = p.stages;
   const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)BN * BK * 2;
   unsigned char* a_s = base;
-  unsigned char* b_s = base + STAGES * a_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(b_s + STAGES * b_bytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);      // [2 samples][BN][2]
+  unsigned char* b_s = base + S * a_bytes;
+  __nv_bfloat16* c_s = reinterpret_cast<__nv_bfloat16*>(b_s + S * b_bytes);            // [128][cpitch] staging
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(c_s + BM * p.cpitch);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* accum_full = empty_bar + S;
+  uint64_t* accum_empty = accum_full + 2;
+  uint64_t* b_bar = accum_empty + 2;                            // resident-weights barrier (cp.async path)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);      // [BN][2]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;           // BN-sized column parts start at multiples of the part width
-  const int ncols = (p.Np - n0 < BN) ? p.Np - n0 : BN;          // valid columns of this tile
+  const int n0 = blockIdx.y * BN;
+  const int ncols = (p.Np - n0 < BN) ? p.Np - n0 : BN;          // valid columns of this column part
+  const int acc_off = p.tmem_cols / 2;                          // TMEM column offset of accumulator 1
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapB) : "memory");
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], p.cpa ? 32 : 1);    // cp.async path: one arrival per producer lane
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&accum_full[b], 1);
+      mbar_init(&accum_empty[b], 4);          // one arrival per epilogue warp
+    }
+    mbar_init(b_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
@@ -187,117 +204,203 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
-  if (STATS && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < 2 * BN * 2; i += NTHREADS - 64) s_stat[i] = 0.f;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // contiguous range of 128-row tiles of this CTA (keeps consecutive tiles in the same sample: statistics
+  // are flushed once per sample, not once per tile)
+  const int tpc = (p.tiles_m + gridDim.x - 1) / gridDim.x;
+  const int tile_begin = blockIdx.x * tpc;
+  const int tile_end = tile_begin + tpc < p.tiles_m ? tile_begin + tpc : p.tiles_m;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      for (int kc = 0; kc < p.nk; ++kc) {
-        const int s = kc % STAGES;
-        const uint32_t ph = (kc / STAGES) & 1;
+    if (p.cpa) {
+      // ===== producer, narrow A (row pitch < 128 B): TMA issues one request per box row and crawls on
+      // 48..112-byte rows, whereas the 128 x Kp tile is ONE contiguous span of global memory.  The warp
+      // copies it with coalesced 16-byte cp.async, scattering every chunk to its SWIZZLE_128B position
+      // (chunk c of row r -> r*128 + ((c ^ (r & 7)) << 4)), i.e. the same canonical K-major layout the
+      // TMA path produces.  B (weights, L2 resident) still comes by TMA.
+      const int cpr = p.Kp >> 3;                                // 16-byte chunks per row (3..7)
+      for (int s = 0; s < S; ++s)                               // chunk columns never written: zero once
+        for (int i = lane; i < BM * (8 - cpr); i += 32) {
+          const int r = i / (8 - cpr), c = cpr + i % (8 - cpr);
+          *reinterpret_cast<uint4*>(a_s + s * a_bytes + r * 128 + ((c ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      // the weights (one K chunk) are loaded ONCE and stay resident: TMA needs ~20 cycles per box row of
+      // this width, which would dominate if repeated per tile
+      if (lane == 0) {
+        mbar_expect_tx(accum_empty + 2, b_bytes);
+        tma_load_2d(b_s, &mapB, accum_empty + 2, 0, n0);
+      }
+      const unsigned char* Ab = reinterpret_cast<const unsigned char*>(A);
+      int it = 0, prev_s = 0;
+      for (int tm = tile_begin; tm < tile_end; ++tm, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
-        tma_load_2d(a_s + s * a_bytes, &mapA, &full_bar[s], kc * BK, m0);
-        tma_load_2d(b_s + s * b_bytes, &mapB, &full_bar[s], kc * BK, n0);
+        const int m0 = tm * BM;
+        const int rows = (p.M - m0 < BM) ? p.M - m0 : BM;
+        const unsigned char* src0 = Ab + (int64_t)m0 * p.Kp * 2;
+        const uint32_t dst0 = smem_u32(a_s + s * a_bytes);
+        for (int ch = lane; ch < BM * cpr; ch += 32) {
+          const int r = ch / cpr, c = ch - r * cpr;
+          const bool ok = r < rows;
+          const unsigned char* src = src0 + (ok ? (int64_t)ch * 16 : 0);
+          const uint32_t dst = dst0 + r * 128 + ((c ^ (r & 7)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        if (it > 0) {                                            // publish the PREVIOUS tile (its copies are done)
+          asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[prev_s])) : "memory");
+        }
+        prev_s = s;
+      }
+      if (it > 0) {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[prev_s])) : "memory");
+      }
+    } else if (lane == 0) {
+      // ===== TMA producer =====
+      int it = 0;
+      for (int tm = tile_begin; tm < tile_end; ++tm) {
+        for (int kc = 0; kc < p.nk; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+          tma_load_2d(a_s + s * a_bytes, &mapA, &full_bar[s], kc * BK, tm * BM);
+          tma_load_2d(b_s + s * b_bytes, &mapB, &full_bar[s], kc * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BN);
-      for (int kc = 0; kc < p.nk; ++kc) {
-        const int s = kc % STAGES;
-        const uint32_t ph = (kc / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, tcount = 0;
+      if (p.cpa && tile_begin < tile_end) mbar_wait(b_bar, 0);
+      for (int tm = tile_begin; tm < tile_end; ++tm, ++tcount) {
+        const int buf = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        mbar_wait(&accum_empty[buf], aph ^ 1u);          // epilogue has drained this accumulator
         tc_fence_after();
-        const int krem = p.Kp - kc * BK;
-        const int ksteps = krem >= BK ? BK / 16 : (krem + 15) / 16;
-        const uint32_t a_addr = smem_u32(a_s + s * a_bytes), b_addr = smem_u32(b_s + s * b_bytes);
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t adesc = make_smem_desc(a_addr + k * 32);
-          const uint64_t bdesc = make_smem_desc(b_addr + k * 32);
-          umma_f16(tmem_base, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
+        const uint32_t tmem_d = tmem_base + buf * acc_off;
+        for (int kc = 0; kc < p.nk; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const int krem = p.Kp - kc * BK;
+          const int ksteps = krem >= BK ? BK / 16 : (krem + 15) / 16;
+          const uint32_t a_addr = smem_u32(a_s + s * a_bytes), b_addr = smem_u32(b_s + (p.cpa ? 0 : s) * b_bytes);
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(tmem_d, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc,
+                     (kc | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);          // ring slot reusable once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);          // ring slot reusable once these MMAs have read it
+        umma_commit(&accum_full[buf]);         // accumulator complete
       }
-      umma_commit(accum_bar);                // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
+    // ===== epilogue: TMEM -> registers -> smem staging -> coalesced global stores (+ column statistics) =====
     const int q = warp & 3;                                // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    __nv_bfloat16* crow = C + (int64_t)row * p.ldc + n0;
-    long long samp = 0;
-    int slot = 0;
-    bool uniform = true;
-    if (STATS) {
-      const long long first = (long long)m0 / p.P_out;
-      samp = (long long)(row_ok ? row : m0) / p.P_out;
-      const long long s0 = __shfl_sync(0xffffffffu, samp, 0);
-      uniform = __all_sync(0xffffffffu, samp == s0 || !row_ok);
-      slot = (int)(s0 - first);
-      if (slot > 1) uniform = false;
-    }
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(taddr + c0, r);
-      if (c0 >= ncols) continue;                           // (warp-uniform) padding columns of the MMA
-      uint32_t w[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-      if (row_ok) {
-        if (c0 + 8 <= ncols) *reinterpret_cast<uint4*>(crow + c0) = make_uint4(w[0], w[1], w[2], w[3]);
-        if (c0 + 16 <= ncols) *reinterpret_cast<uint4*>(crow + c0 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-      }
-      if (STATS) {
-        float v[16], v2[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[2 * j] = row_ok ? __uint_as_float(w[j] << 16) : 0.f;
-          v[2 * j + 1] = row_ok ? __uint_as_float(w[j] & 0xffff0000u) : 0.f;
+    const int et = threadIdx.x - 64;                       // 0..127 among the epilogue threads
+    const int rloc = q * 32 + lane;                        // row of the tile owned by this thread
+    // statistics: per-CTA accumulators s_stat[col][2] of the sample `cur_samp`; flushed to global (fp64
+    // atomics) only when the CTA's contiguous tile range moves on to another sample
+    long long cur_samp = -1;
+    auto flush_stats = [&]() {
+      if (cur_samp >= 0) {
+        for (int i = et; i < BN * 2; i += 128) {
+          const int col = i >> 1;
+          const float v = s_stat[i];
+          if (col < ncols && v != 0.f) atomicAdd(&stats[(cur_samp * p.ldc + n0 + col) * 2 + (i & 1)], (double)v);
+          s_stat[i] = 0.f;
         }
+      }
+    };
+    if (STATS) {
+      for (int i = et; i < BN * 2; i += 128) s_stat[i] = 0.f;
+    }
+    int tcount = 0;
+    for (int tm = tile_begin; tm < tile_end; ++tm, ++tcount) {
+      const int buf = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      const int m0 = tm * BM;
+      // staging buffer is free (previous tile fully copied out / summed)
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      mbar_wait(&accum_full[buf], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * acc_off + ((uint32_t)(q * 32) << 16);
+      __nv_bfloat16* srow = c_s + rloc * p.cpitch;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        if (c0 >= ncols || (p.dbg & 4)) continue;          // (warp-uniform) padding columns of the MMA
+        uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v2[j] = v[j] * v[j];
-        if (uniform) {
-          const float s1 = butterfly16(v, lane);
-          const float s2 = butterfly16(v2, lane);
-          const int col = c0 + butterfly_col(lane);
-          if ((lane & 1) == 0 && col < ncols) {
-            atomicAdd(&s_stat[(slot * BN + col) * 2 + 0], s1);
-            atomicAdd(&s_stat[(slot * BN + col) * 2 + 1], s2);
+        for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        *reinterpret_cast<uint4*>(srow + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(srow + c0 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&accum_empty[buf])) : "memory");
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");     // tile staged in shared memory
+      // coalesced copy-out: consecutive threads write consecutive 16-byte chunks of the output rows
+      const int rows_valid = (p.M - m0 < BM) ? p.M - m0 : BM;
+      const int cpr = ncols >> 3;                            // 16-byte chunks per row
+      const int nchunks = rows_valid * cpr;
+      for (int ch = et; ch < ((p.dbg & 1) ? 0 : nchunks); ch += 128) {
+        const int r = ch / cpr, cc = ch - r * cpr;
+        const uint4 v = *reinterpret_cast<const uint4*>(c_s + r * p.cpitch + cc * 8);
+        *reinterpret_cast<uint4*>(C + (int64_t)(m0 + r) * p.ldc + n0 + cc * 8) = v;
+      }
+      if (STATS && !(p.dbg & 2)) {
+        // column sums of the staged (bf16-rounded) tile, one row segment per sample touched by the tile:
+        // thread = (column pair, row group); conflict-free 4-byte shared loads, no shuffles
+        const int npair = ncols >> 1;
+        const int groups = 128 / npair > 0 ? 128 / npair : 1;        // row groups working on a column pair
+        const int cp = et % npair, grp = et / npair;
+        int r0 = 0;
+        while (r0 < rows_valid) {
+          const long long samp = (long long)(m0 + r0) / p.P_out;
+          long long lim = (samp + 1) * p.P_out - m0;                // first row of the next sample (tile-local)
+          const int r1 = lim < rows_valid ? (int)lim : rows_valid;
+          if (samp != cur_samp) {                                   // uniform across the 128 threads
+            asm volatile("bar.sync 2, 128;\n" ::: "memory");        // everybody's atomics of the old sample landed
+            flush_stats();
+            cur_samp = samp;
+            asm volatile("bar.sync 2, 128;\n" ::: "memory");
           }
-        } else if (row_ok) {
-          // tile straddles more than two samples (tiny feature maps): rare, per-element fp64 atomics
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (c0 + j < ncols) {
-              double* gp = stats + (samp * p.ldc + n0 + c0 + j) * 2;
-              atomicAdd(gp, (double)v[j]);
-              atomicAdd(gp + 1, (double)v2[j]);
+          if (et < npair * groups) {
+            float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f;
+            for (int r = r0 + grp; r < r1; r += groups) {
+              const uint32_t wv = *reinterpret_cast<const uint32_t*>(c_s + r * p.cpitch + 2 * cp);
+              const float a = __uint_as_float(wv << 16), b2 = __uint_as_float(wv & 0xffff0000u);
+              s1x += a; s1y += b2;
+              s2x = fmaf(a, a, s2x); s2y = fmaf(b2, b2, s2y);
             }
+            atomicAdd(&s_stat[(2 * cp) * 2 + 0], s1x);
+            atomicAdd(&s_stat[(2 * cp) * 2 + 1], s2x);
+            atomicAdd(&s_stat[(2 * cp + 1) * 2 + 0], s1y);
+            atomicAdd(&s_stat[(2 * cp + 1) * 2 + 1], s2y);
           }
+          r0 = r1;
         }
       }
     }
     if (STATS) {
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");     // the four epilogue warps
-      const long long first = (long long)m0 / p.P_out;
-      for (int i = threadIdx.x - 64; i < 2 * BN * 2; i += 128) {
-        const int sl = i / (BN * 2), rem = i % (BN * 2), col = rem >> 1;
-        const float v = s_stat[i];
-        if (col < ncols && v != 0.f)
-          atomicAdd(&stats[((first + sl) * p.ldc + n0 + col) * 2 + (rem & 1)], (double)v);
-      }
+      asm volatile("bar.sync 2, 128;\n" ::: "memory");
+      flush_stats();
     }
   }
   tc_fence_before();
@@ -503,6 +606,9 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
   int64_t msplit = (2 * kNumSMs + ntiles * kz - 1) / (ntiles * kz);
   const int64_t max_split = (M + 511) / 512;
   if (msplit > max_split) msplit = max_split;
+  // every CTA ends with one fp32 red per element of its dW tile: keep the total under ~2M reds
+  const int64_t red_cap = 2000000 / (Np * Kp) > 1 ? 2000000 / (Np * Kp) : 1;
+  if (msplit > red_cap) msplit = red_cap;
   if (msplit < 1) msplit = 1;
   int64_t rpc = ((M + msplit - 1) / msplit + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
   msplit = (M + rpc - 1) / rpc;
@@ -537,27 +643,48 @@ int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, 
   if (M < 1 || Kp % 8 || Np % 8 || M >= (1ll << 31)) return 0;
   // column tiles of width BN (multiple of 16, <= 256): the whole N when it fits one MMA, else N split in
   // near-equal parts; tile j covers columns [j*BN, min((j+1)*BN, Np)), weight rows beyond Np are TMA zero fill
-  const int parts = (int)((Np + 255) / 256);
+  // <= 128 columns per CTA: accumulators take <= 256 TMEM columns, so >= 2 CTAs (8 epilogue warps) per SM
+  static const int max_bn = getenv("X3D_TC_MAXBN") ? atoi(getenv("X3D_TC_MAXBN")) : 128;
+  const int parts = (int)((Np + max_bn - 1) / max_bn);
   const int BN = (int)(((Np + parts - 1) / parts + 15) / 16 * 16);
   if (BN > 256) return 0;
   TcParams p;
   p.M = (int)M; p.Kp = (int)Kp; p.Np = (int)Np; p.BN = BN; p.ldc = (int)Np;
   p.nk = (int)((Kp + BK - 1) / BK);
-  p.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  // two accumulators of BN fp32 columns each
+  p.tmem_cols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   p.P_out = P_out;
+  p.tiles_m = (int)((M + BM - 1) / BM);
+  p.cpitch = BN + 8;
+  static const int dbg = getenv("X3D_TC_DBG") ? atoi(getenv("X3D_TC_DBG")) : 0;
+  p.dbg = dbg;
+  static const bool no_cpa = getenv("X3D_TC_NOCPA") != nullptr;
+  p.cpa = (Kp < BK && !no_cpa) ? 1 : 0;
+  p.stages = BN > 128 ? 3 : 2;      // small-N layers: 2 stages so that 2-3 CTAs fit per SM (nk is 1-2 there)
   CUtensorMap mapA, mapB;
   if (!make_map_2d(&mapA, x, M, Kp, BM)) return 0;
   if (!make_map_2d(&mapB, w, Np, Kp, BN)) return 0;
-  const size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + (size_t)BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 +
-                      (stats ? (size_t)2 * BN * 2 * sizeof(float) : 0);
-  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((Np + BN - 1) / BN));
+  const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + (size_t)BN * BK * 2) + (size_t)BM * p.cpitch * 2 +
+                      (2 * p.stages + 6) * 8 + 16 + (size_t)2 * BN * 2 * sizeof(float);
+  // resident CTAs: TMEM (512 columns per SM) and shared memory (227 KB per SM) bound the co-residency
+  int per_sm = 512 / p.tmem_cols;
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > by_smem) per_sm = by_smem;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 3) per_sm = 3;
+  const int parts_n = (int)((Np + BN - 1) / BN);
+  int gx = (kNumSMs * per_sm) / parts_n;
+  if (gx < 1) gx = 1;
+  if (gx > p.tiles_m) gx = p.tiles_m;
+  gx = (p.tiles_m + (p.tiles_m + gx - 1) / gx - 1) / ((p.tiles_m + gx - 1) / gx);   // no empty CTAs
+  dim3 grid((unsigned)gx, (unsigned)parts_n);
   static bool attr_done[2] = {false, false};
   if (stats) {
     if (!attr_done[1]) { cudaFuncSetAttribute(pw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done[1] = true; }
-    pw_tc_kernel<true><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, (__nv_bfloat16*)y, p, stats);
+    pw_tc_kernel<true><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, p, stats);
   } else {
     if (!attr_done[0]) { cudaFuncSetAttribute(pw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done[0] = true; }
-    pw_tc_kernel<false><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, (__nv_bfloat16*)y, p, nullptr);
+    pw_tc_kernel<false><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, p, nullptr);
   }
   *handled = true;
   cudaError_t e = cudaGetLastError();

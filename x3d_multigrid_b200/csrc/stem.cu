@@ -87,7 +87,7 @@ extern "C" int x3d_stem_conv_s_fwd(const float* x, const float* w, void* y, int6
 }
 
 // wgrad: dw[co][tap] += sum_p dy[p][co] * xcol[p][tap].  Block: 256 threads = 32 taps x 8 channel groups.
-constexpr int SW_POS = 64;
+constexpr int SW_POS = 128;
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                           float* __restrict__ dw, int Ci, int T_, int H, int W,
@@ -97,11 +97,18 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   float* Xs = sm;                   // [SW_POS][32]
   float* Ds = sm + SW_POS * 32;     // [SW_POS][Cop]
   const int taps = Ci * 9;
-  const int tap = threadIdx.x / 8, cg = threadIdx.x % 8;
-  const int cpt = Cop / 8;          // channels per thread (3 or 4 ...)
-  float acc[8];
+  // register tile: a thread owns 3 taps x 8 channels and every `nslice`-th position of the tile
+  const int ncg = Cop / 8;                      // channel groups
+  const int roles = 9 * ncg;                    // (tap group, channel group) pairs
+  const int nslice = 256 / roles;
+  const int role = threadIdx.x % roles, slice = threadIdx.x / roles;
+  const int tg = role % 9, cg = role / 9;
+  const bool active = slice < nslice && tg * 3 < taps;
+  float acc[3][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   const int64_t pb = (int64_t)blockIdx.x * pos_per_block;
   const int64_t pe = (pb + pos_per_block < total) ? pb + pos_per_block : total;
   for (int64_t ps = pb; ps < pe; ps += SW_POS) {
@@ -129,24 +136,39 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
       Ds[i] = (p < pe) ? to_float<T>(dy[p * Cop + (i % Cop)]) : 0.f;
     }
     __syncthreads();
-    if (tap < taps) {
-#pragma unroll 4
-      for (int pp = 0; pp < SW_POS; ++pp) {
-        const float xv = Xs[pp * 32 + tap];
-        const float* dp = &Ds[pp * Cop + cg * cpt];
+    if (active) {
+#pragma unroll 2
+      for (int pp = slice; pp < SW_POS; pp += nslice) {
+        const float* xp = &Xs[pp * 32 + tg * 3];
+        const float x0 = xp[0], x1 = xp[1], x2 = xp[2];
+        const float4 d0 = *reinterpret_cast<const float4*>(&Ds[pp * Cop + cg * 8]);
+        const float4 d1 = *reinterpret_cast<const float4*>(&Ds[pp * Cop + cg * 8 + 4]);
+        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < cpt) acc[j] = fmaf(xv, dp[j], acc[j]);
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] = fmaf(x0, d[j], acc[0][j]);
+          acc[1][j] = fmaf(x1, d[j], acc[1][j]);
+          acc[2][j] = fmaf(x2, d[j], acc[2][j]);
+        }
       }
     }
     __syncthreads();
   }
-  if (tap < taps) {
+  // slices -> shared (reuse Xs as [taps][Cop] accumulators) -> one atomic per (channel, tap) per block
+  float* red = Xs;
+  for (int i = threadIdx.x; i < 32 * Cop; i += 256) red[i] = 0.f;
+  __syncthreads();
+  if (active) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cg * cpt + j;
-      if (j < cpt && c < Co && acc[j] != 0.f) atomicAdd(&dw[(int64_t)c * taps + tap], acc[j]);
-    }
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&red[(tg * 3 + i) * Cop + cg * 8 + j], acc[i][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < taps * Cop; i += 256) {
+    const int tap = i / Cop, c = i % Cop;
+    const float v = red[i];
+    if (c < Co && v != 0.f) atomicAdd(&dw[(int64_t)c * taps + tap], v);
   }
 }
 
