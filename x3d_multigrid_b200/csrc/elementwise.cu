@@ -949,13 +949,92 @@ __global__ void small_gemm_kernel(const float* __restrict__ A, int64_t sai, int6
     }
   }
 }
+// skinny variants for M <= 32 rows (the head: M = batch): the 32x32-tile kernel would run on a handful of CTAs
+// (a) B k-contiguous (sbk == 1): one warp per output column, lanes split K, shuffle reduction
+template <int MR>
+__global__ void skinny_gemm_kcontig_kernel(const float* __restrict__ A, int64_t sai, int64_t sak,
+                                           const float* __restrict__ B, int64_t sbj, float* __restrict__ C, int64_t ldc,
+                                           int M, int Nn, int K, const float* __restrict__ bias, int relu,
+                                           const float* __restrict__ mul, int accumulate) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= Nn) return;
+  const int j = warp;
+  float acc[MR];
+#pragma unroll
+  for (int i = 0; i < MR; ++i) acc[i] = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float b = B[(int64_t)j * sbj + k];
+#pragma unroll
+    for (int i = 0; i < MR; ++i)
+      if (i < M) acc[i] = fmaf(A[(int64_t)i * sai + (int64_t)k * sak], b, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < MR; ++i) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < MR; ++i) {
+      if (i < M) {
+        float v = acc[i] + (bias ? bias[j] : 0.f);
+        if (relu) v = fmaxf(v, 0.f);
+        if (mul) v *= mul[(int64_t)i * Nn + j];
+        float* dst = &C[(int64_t)i * ldc + j];
+        *dst = accumulate ? (*dst + v) : v;
+      }
+    }
+  }
+}
+// (b) B j-contiguous (sbj == 1): one thread per output column, loop over K (A broadcast through L1)
+template <int MR>
+__global__ void skinny_gemm_jcontig_kernel(const float* __restrict__ A, int64_t sai, int64_t sak,
+                                           const float* __restrict__ B, int64_t sbk, float* __restrict__ C, int64_t ldc,
+                                           int M, int Nn, int K, const float* __restrict__ bias, int relu,
+                                           const float* __restrict__ mul, int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Nn) return;
+  float acc[MR];
+#pragma unroll
+  for (int i = 0; i < MR; ++i) acc[i] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float b = B[(int64_t)k * sbk + j];
+#pragma unroll
+    for (int i = 0; i < MR; ++i)
+      if (i < M) acc[i] = fmaf(A[(int64_t)i * sai + (int64_t)k * sak], b, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < MR; ++i) {
+    if (i < M) {
+      float v = acc[i] + (bias ? bias[j] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      if (mul) v *= mul[(int64_t)i * Nn + j];
+      float* dst = &C[(int64_t)i * ldc + j];
+      *dst = accumulate ? (*dst + v) : v;
+    }
+  }
+}
+
 extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
                               float* C, int64_t ldc, int64_t M, int64_t Nn, int64_t K, const float* bias, int relu,
                               const float* mul, int accumulate, x3d_stream_t stream) {
   if (M == 0 || Nn == 0) return 0;
-  dim3 grid((unsigned)cdiv(Nn, 32), (unsigned)cdiv(M, 32)), block(32, 8);
-  small_gemm_kernel<<<grid, block, 0, as_stream(stream)>>>(A, sai, sak, B, sbk, sbj, C, ldc, (int)M, (int)Nn, (int)K,
-                                                          bias, relu, mul, accumulate);
+  if (M <= 32 && sbk == 1) {
+    const int64_t threads = Nn * 32;
+#define SK_(MR) skinny_gemm_kcontig_kernel<MR><<<(unsigned)cdiv(threads, 256), 256, 0, as_stream(stream)>>>( \
+      A, sai, sak, B, sbj, C, ldc, (int)M, (int)Nn, (int)K, bias, relu, mul, accumulate)
+    if (M <= 8) SK_(8); else if (M <= 16) SK_(16); else SK_(32);
+#undef SK_
+  } else if (M <= 32 && sbj == 1) {
+#define SJ_(MR) skinny_gemm_jcontig_kernel<MR><<<(unsigned)cdiv(Nn, 64), 64, 0, as_stream(stream)>>>( \
+      A, sai, sak, B, sbk, C, ldc, (int)M, (int)Nn, (int)K, bias, relu, mul, accumulate)
+    if (M <= 8) SJ_(8); else if (M <= 16) SJ_(16); else SJ_(32);
+#undef SJ_
+  } else {
+    dim3 grid((unsigned)cdiv(Nn, 32), (unsigned)cdiv(M, 32)), block(32, 8);
+    small_gemm_kernel<<<grid, block, 0, as_stream(stream)>>>(A, sai, sak, B, sbk, sbj, C, ldc, (int)M, (int)Nn, (int)K,
+                                                            bias, relu, mul, accumulate);
+  }
   X3D_LAUNCH_CHECK();
   return 0;
 }
