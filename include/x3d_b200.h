@@ -199,6 +199,10 @@ typedef struct {
 int x3d_sgd_step(const x3d_sgd_desc_t* descs_dev, int n_desc, int64_t max_numel, float lr,
                  float momentum, float weight_decay, float grad_scale, int first_step,
                  x3d_stream_t stream);
+/* same, hyper-parameters read from device memory hyper_dev = {lr, momentum, weight_decay, grad_scale}: lets a
+ * captured CUDA graph follow LR schedules (the long-cycle LR law, train_x3d_kinetics_multigrid.py:229-233) */
+int x3d_sgd_step_dev(const x3d_sgd_desc_t* descs_dev, int n_desc, int64_t max_numel, const float* hyper_dev,
+                     int first_step, x3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1075,7 +1075,8 @@ extern "C" int x3d_relu_mask_mul(const float* src, const float* ref, const float
 // fused SGD (momentum, weight decay; torch.optim.SGD semantics, dampening 0, no nesterov)
 // =======================================================================================
 __global__ void sgd_kernel(const x3d_sgd_desc_t* __restrict__ descs, float lr, float momentum, float wd,
-                           float grad_scale, int first_step) {
+                           float grad_scale, int first_step, const float* __restrict__ hyper) {
+  if (hyper) { lr = hyper[0]; momentum = hyper[1]; wd = hyper[2]; grad_scale = hyper[3]; }
   const x3d_sgd_desc_t d = descs[blockIdx.y];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.numel; i += (int64_t)gridDim.x * blockDim.x) {
     float p = d.param[i];
@@ -1096,7 +1097,19 @@ extern "C" int x3d_sgd_step(const x3d_sgd_desc_t* descs_dev, int n_desc, int64_t
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
   sgd_kernel<<<dim3((unsigned)bx, (unsigned)n_desc), 256, 0, as_stream(stream)>>>(descs_dev, lr, momentum, weight_decay,
-                                                                              grad_scale, first_step);
+                                                                              grad_scale, first_step, nullptr);
+  X3D_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int x3d_sgd_step_dev(const x3d_sgd_desc_t* descs_dev, int n_desc, int64_t max_numel, const float* hyper_dev,
+                                int first_step, x3d_stream_t stream) {
+  if (n_desc == 0) return 0;
+  X3D_CHECK_ARG(hyper_dev != nullptr, "hyper_dev");
+  int64_t bx = cdiv(max_numel, 256 * 4);
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  sgd_kernel<<<dim3((unsigned)bx, (unsigned)n_desc), 256, 0, as_stream(stream)>>>(descs_dev, 0.f, 0.f, 0.f, 1.f, first_step,
+                                                                              hyper_dev);
   X3D_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,58 @@
+"""CUDA-graph capture of one whole training step (forward, loss, backward, optimizer) per clip shape.
+
+A training step of X3D-M is ~700 kernel launches of 2-400 microseconds; replaying them as one CUDA graph
+removes the host from the critical path.  The multigrid schedule (kinetics_multigrid.py:205-237) alternates
+between 2-3 shapes inside a long cycle: keep one ``GraphedTrainStep`` per (B, T, H, W).
+
+    step = GraphedTrainStep(model, optimizer, criterion, example_clip, example_labels)
+    loss = step(clip, labels)          # copies into the static buffers (async), replays, returns the loss tensor
+
+``optimizer`` should be ``optim.FusedSGD(..., capturable=True)`` so that LR changes reach the graph
+(call ``optimizer.sync_hyper()`` after editing ``param_groups``)."""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, criterion, example_x, example_y, warmup=3):
+        self.model, self.opt, self.crit = model, optimizer, criterion
+        dev = example_x.device
+        self.static_x = torch.empty_like(example_x, device=dev)
+        self.static_y = torch.empty_like(example_y, device=dev)
+        self.static_x.copy_(example_x)
+        self.static_y.copy_(example_y)
+        # warm-up on a side stream (allocator pools, parameter tables, kernel attributes, arena sizes)
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._one_step()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._one_step()
+        torch.cuda.synchronize(dev)
+
+    def _one_step(self):
+        self.opt.zero_grad(set_to_none=True)
+        logits = self.model(self.static_x)
+        loss = self.crit(logits, self.static_y)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, x, y):
+        if x.shape != self.static_x.shape:
+            raise RuntimeError('GraphedTrainStep is bound to one clip shape; keep one instance per multigrid shape')
+        self.static_x.copy_(x, non_blocking=True)
+        self.static_y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss
+
+    def replay(self):
+        """replay on whatever currently sits in static_x / static_y (inputs staged by the caller)"""
+        self.graph.replay()
+        return self.static_loss

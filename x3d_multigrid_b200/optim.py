@@ -3,7 +3,11 @@
 Same update rule as ``torch.optim.SGD(params, lr, momentum, weight_decay)`` as used by the
 reference loop (train_x3d_kinetics_multigrid.py:183,277): d = g*grad_scale + wd*p;
 buf = d (first step) | momentum*buf + d;  p -= lr*buf.  One param group semantics are kept
-(``param_groups[0]['lr']`` can be edited by LR schedulers / the long-cycle LR law)."""
+(``param_groups[0]['lr']`` can be edited by LR schedulers / the long-cycle LR law).
+
+``capturable=True`` reads the hyper-parameters from a small device tensor, so that a captured
+CUDA graph (graphs.GraphedTrainStep) follows later LR changes: call ``sync_hyper()`` (a 16-byte
+H2D copy) before a replay whenever ``param_groups`` changed."""
 from __future__ import annotations
 
 import torch
@@ -13,19 +17,20 @@ from ._lib import SgdDesc
 
 
 class FusedSGD(torch.optim.Optimizer):
-    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, capturable=False):
         super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
         self._tables = {}
         self.grad_scale = 1.0       # e.g. 1/world_size when gradients were summed, not averaged
+        self.capturable = capturable
+        self._hyper = {}            # group index -> (device tensor, pinned host tensor)
 
     def _table(self, gi, group):
         ps = [p for p in group['params'] if p.grad is not None]
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        key = tuple(p.grad.data_ptr() for p in ps)
         tab = self._tables.get(gi)
         if tab is not None and tab[0] == key:
             return tab
-        first = False
-        arr = (SgdDesc * len(ps))()
+        arr = (SgdDesc * max(len(ps), 1))()
         mx = 1
         for i, p in enumerate(ps):
             if p.dtype != torch.float32 or not p.is_cuda:
@@ -34,14 +39,36 @@ class FusedSGD(torch.optim.Optimizer):
             if 'momentum_buffer' not in st:
                 st['momentum_buffer'] = torch.zeros_like(p)
                 st['fresh'] = True
-                first = True
-            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-            arr[i] = SgdDesc(p.data_ptr(), g.data_ptr(), st['momentum_buffer'].data_ptr(), p.numel())
+            if not p.grad.is_contiguous():
+                raise RuntimeError('FusedSGD needs contiguous gradients')
+            arr[i] = SgdDesc(p.data_ptr(), p.grad.data_ptr(), st['momentum_buffer'].data_ptr(), p.numel())
             mx = max(mx, p.numel())
-        dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(ps[0].device) if ps else None
-        tab = (key, dev, len(ps), mx, ps)
+        dev = host = None
+        if ps:
+            # pinned staging + async copy: legal inside CUDA-graph capture (the host buffer stays alive in the table)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+            dev = torch.empty(host.numel(), dtype=torch.uint8, device=ps[0].device)
+            dev.copy_(host, non_blocking=True)
+        tab = (key, dev, len(ps), mx, ps, host)
         self._tables[gi] = tab
         return tab
+
+    def sync_hyper(self):
+        """push lr / momentum / weight_decay / grad_scale of every group to the device (capturable mode)"""
+        for gi, group in enumerate(self.param_groups):
+            if gi in self._hyper:
+                dev, host = self._hyper[gi]
+                host[0], host[1] = float(group['lr']), float(group['momentum'])
+                host[2], host[3] = float(group['weight_decay']), float(self.grad_scale)
+                dev.copy_(host, non_blocking=True)
+
+    def _hyper_dev(self, gi, group, device):
+        if gi not in self._hyper:
+            host = torch.zeros(4, dtype=torch.float32).pin_memory()
+            dev = torch.zeros(4, dtype=torch.float32, device=device)
+            self._hyper[gi] = (dev, host)
+            self.sync_hyper()
+        return self._hyper[gi][0]
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -51,7 +78,7 @@ class FusedSGD(torch.optim.Optimizer):
                 loss = closure()
         L = _lib.lib()
         for gi, group in enumerate(self.param_groups):
-            key, dev, n, mx, ps = self._table(gi, group)
+            key, dev, n, mx, ps, _host = self._table(gi, group)
             if n == 0:
                 continue
             fresh = [self.state[p].get('fresh', False) for p in ps]
@@ -59,8 +86,12 @@ class FusedSGD(torch.optim.Optimizer):
                 raise RuntimeError('FusedSGD: parameters joined the group after the first step')
             first = all(fresh)
             st = torch.cuda.current_stream(ps[0].device).cuda_stream
-            L.call('x3d_sgd_step', dev.data_ptr(), n, mx, float(group['lr']), float(group['momentum']),
-                   float(group['weight_decay']), float(self.grad_scale), 1 if first else 0, st)
+            if self.capturable:
+                hy = self._hyper_dev(gi, group, ps[0].device)
+                L.call('x3d_sgd_step_dev', dev.data_ptr(), n, mx, hy.data_ptr(), 1 if first else 0, st)
+            else:
+                L.call('x3d_sgd_step', dev.data_ptr(), n, mx, float(group['lr']), float(group['momentum']),
+                       float(group['weight_decay']), float(self.grad_scale), 1 if first else 0, st)
             if first:
                 for p in ps:
                     self.state[p]['fresh'] = False
