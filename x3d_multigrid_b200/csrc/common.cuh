@@ -117,7 +117,7 @@ __device__ __forceinline__ float from_float<float>(float x) { return x; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // dispatch on the activation dtype
 #define X3D_DISPATCH_DTYPE(dt, ...)                         \
@@ -164,20 +164,24 @@ static inline RowGeom make_row_geom(int64_t N, int64_t P, int64_t Cp, int target
 }
 
 // Block-level reduction of per-thread channel accumulators into double stats[n][Cp][2].
-// acc0/acc1: VEC partial sums owned by this thread for channels [cvec*VEC, +VEC).
+// acc0/acc1: VEC partial sums owned by this thread for channels [cvec*VEC, +VEC).  Block = cv x rows threads
+// (thread = cvec + cv*prow).  Every thread parks its partials in its own shared slot (no atomics), then one
+// thread per (channel, quantity) sums the `rows` slots and issues ONE fp64 atomic.  s_acc: rows*Cp*2 floats.
 template <int VEC>
 __device__ __forceinline__ void block_stats_flush(float (&acc0)[VEC], float (&acc1)[VEC], int cvec, int Cp,
-                                                  float* s_acc /* [Cp*2] smem */, double* stats_n /* [Cp][2] */) {
-  for (int i = threadIdx.x; i < Cp * 2; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+                                                  float* s_acc, double* stats_n /* [Cp][2] */) {
+  const int cv = Cp / VEC;
+  const int prow = threadIdx.x / cv, rows = blockDim.x / cv;
+  float* mine = s_acc + (size_t)prow * Cp * 2;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    atomicAdd(&s_acc[(cvec * VEC + j) * 2 + 0], acc0[j]);
-    atomicAdd(&s_acc[(cvec * VEC + j) * 2 + 1], acc1[j]);
+    mine[(cvec * VEC + j) * 2 + 0] = acc0[j];
+    mine[(cvec * VEC + j) * 2 + 1] = acc1[j];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < Cp * 2; i += blockDim.x) {
-    float v = s_acc[i];
+    float v = 0.f;
+    for (int r = 0; r < rows; ++r) v += s_acc[(size_t)r * Cp * 2 + i];
     if (v != 0.f) atomicAdd(&stats_n[i], (double)v);
   }
 }

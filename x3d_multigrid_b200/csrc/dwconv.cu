@@ -109,7 +109,7 @@ static int launch_dw_fwd_direct(const void* x, const float* w, void* y, int64_t 
   const int64_t P = (int64_t)g.T * g.Ho * g.Wo;
   RowGeom rg = make_row_geom<T>(N, P, g.Cp, 8 * kNumSMs);
   dim3 grid(rg.chunks, (unsigned)N);
-  size_t smem = stats ? g.Cp * 2 * sizeof(float) : 0;
+  size_t smem = stats ? (size_t)rg.rows * g.Cp * 2 * sizeof(float) : 0;
 #define L_(XF, RL, ST)                                                                                          \
   dw_fwd_direct_kernel<T, KT, KH, KW, XF, RL, ST><<<grid, rg.threads, smem, stream>>>(                          \
       (const T*)x, w, (T*)y, g, scale, shift, splits, stats, P, rg.cv, rg.rows, rg.chunk)
@@ -259,7 +259,7 @@ extern "C" int x3d_dwconv_dgrad(const void* dy, const float* w_packed, void* dx,
   X3D_DISPATCH_DTYPE(dt, {
     RowGeom rg = make_row_geom<T>(N, P, Cp, 8 * kNumSMs);
     dim3 grid(rg.chunks, (unsigned)N);
-    size_t smem = mask_src ? Cp * 2 * sizeof(float) : 0;
+    size_t smem = mask_src ? (size_t)rg.rows * Cp * 2 * sizeof(float) : 0;
     if (kt == 3 && mask_src) L_(3, 3, 3, true);
     else if (kt == 3) L_(3, 3, 3, false);
     else if (mask_src) L_(5, 1, 1, true);

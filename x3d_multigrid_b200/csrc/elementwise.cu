@@ -131,6 +131,28 @@ extern "C" int x3d_pack_params(const x3d_pack_desc_t* descs_dev, int n_desc, int
 // =======================================================================================
 // split-BN finalize: per-sample sums -> per-(split,channel) scale/shift + running stats
 // =======================================================================================
+// sum of the per-sample {s1, s2} pairs of split b, channel c: 16-byte loads, 4 independent accumulators so that
+// the (cold) global loads overlap instead of forming one dependent chain
+__device__ __forceinline__ void sum_split(const double* __restrict__ stats, int N, int splits, int b, int c, int Cp,
+                                          double& s1, double& s2) {
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+  const double2* p = reinterpret_cast<const double2*>(stats) + ((int64_t)b * Cp + c);
+  const int64_t step = (int64_t)splits * Cp;
+  const int cnt = (N - b + splits - 1) / splits;
+  int i = 0;
+  for (; i + 4 <= cnt; i += 4) {
+    const double2 v0 = __ldg(p + (int64_t)(i + 0) * step), v1 = __ldg(p + (int64_t)(i + 1) * step);
+    const double2 v2 = __ldg(p + (int64_t)(i + 2) * step), v3 = __ldg(p + (int64_t)(i + 3) * step);
+    a0 += v0.x; a1 += v0.y; b0 += v1.x; b1 += v1.y; c0 += v2.x; c1 += v2.y; d0 += v3.x; d1 += v3.y;
+  }
+  for (; i < cnt; ++i) {
+    const double2 v = __ldg(p + (int64_t)i * step);
+    a0 += v.x; a1 += v.y;
+  }
+  s1 = (a0 + b0) + (c0 + d0);
+  s2 = (a1 + b1) + (c1 + d1);
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int splits, double P, int C, int Cp,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ run_mean, float* __restrict__ run_var,
@@ -145,11 +167,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int 
     scale[idx] = 0.f; shift[idx] = 0.f; mean_o[idx] = 0.f; rstd_o[idx] = 0.f;
     return;
   }
-  double s1 = 0.0, s2 = 0.0;
-  for (int n = b; n < N; n += splits) {
-    s1 += stats[((int64_t)n * Cp + c) * 2 + 0];
-    s2 += stats[((int64_t)n * Cp + c) * 2 + 1];
-  }
+  double s1, s2;
+  sum_split(stats, N, splits, b, c, Cp, s1, s2);
   const double m = (double)(N / splits) * P;
   const double mu = s1 / m;
   double var = s2 / m - mu * mu;
@@ -299,7 +318,7 @@ extern "C" int x3d_bn_bwd_reduce(const void* dout, const void* mask_out, const v
   X3D_DISPATCH_DTYPE(dt, {
     RowGeom g = make_row_geom<T>(N, P, Cp);
     dim3 grid(g.chunks, (unsigned)N);
-    size_t smem = Cp * 2 * sizeof(float);
+    size_t smem = (size_t)g.rows * Cp * 2 * sizeof(float);
     if (mask_out)
       bn_bwd_reduce_kernel<T, true><<<grid, g.threads, smem, as_stream(stream)>>>(
           (const T*)dout, (const T*)mask_out, (const T*)a, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
@@ -316,45 +335,37 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int N, 
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ rstd, int train, float* __restrict__ coef,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Cp) return;
+  // one thread per (split, channel)
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int sC = splits * Cp;
+  if (idx >= sC) return;
+  const int b = idx / Cp, c = idx % Cp;
   if (c >= C) {
-    for (int b = 0; b < splits; ++b) {
-      coef[0 * sC + b * Cp + c] = 0.f; coef[1 * sC + b * Cp + c] = 0.f; coef[2 * sC + b * Cp + c] = 0.f;
-    }
+    coef[0 * sC + idx] = 0.f; coef[1 * sC + idx] = 0.f; coef[2 * sC + idx] = 0.f;
     return;
   }
   const double g = gamma[c];
   const double m = (double)(N / splits) * P;
-  double dg = 0.0, db = 0.0;
-  for (int b = 0; b < splits; ++b) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int n = b; n < N; n += splits) {
-      s1 += stats[((int64_t)n * Cp + c) * 2 + 0];
-      s2 += stats[((int64_t)n * Cp + c) * 2 + 1];
-    }
-    const double mu = mean[b * Cp + c], r = rstd[b * Cp + c];
-    const double sxh = (s2 - mu * s1) * r;  // sum dpre * xhat
-    dg += sxh;
-    db += s1;
-    double A = g * r, B = 0.0, Cc = 0.0;
-    if (train) {
-      const double m1 = s1 / m, m2 = sxh / m;
-      B = -g * r * r * m2;
-      Cc = g * r * (-m1 + mu * r * m2);
-    }
-    coef[0 * sC + b * Cp + c] = (float)A;
-    coef[1 * sC + b * Cp + c] = (float)B;
-    coef[2 * sC + b * Cp + c] = (float)Cc;
+  double s1, s2;
+  sum_split(stats, N, splits, b, c, Cp, s1, s2);
+  const double mu = mean[idx], r = rstd[idx];
+  const double sxh = (s2 - mu * s1) * r;  // sum dpre * xhat
+  double A = g * r, B = 0.0, Cc = 0.0;
+  if (train) {
+    const double m1 = s1 / m, m2 = sxh / m;
+    B = -g * r * r * m2;
+    Cc = g * r * (-m1 + mu * r * m2);
   }
-  if (dgamma) dgamma[c] += (float)dg;
-  if (dbeta) dbeta[c] += (float)db;
+  coef[0 * sC + idx] = (float)A;
+  coef[1 * sC + idx] = (float)B;
+  coef[2 * sC + idx] = (float)Cc;
+  if (dgamma) atomicAdd(&dgamma[c], (float)sxh);
+  if (dbeta) atomicAdd(&dbeta[c], (float)s1);
 }
 extern "C" int x3d_bn_bwd_finalize(const double* stats, int64_t N, int splits, int64_t P, int64_t C, int64_t Cp,
                                    const float* gamma, const float* mean, const float* rstd, int train,
                                    float* coef, float* dgamma, float* dbeta, x3d_stream_t stream) {
-  bn_bwd_finalize_kernel<<<(unsigned)cdiv(Cp, 64), 64, 0, as_stream(stream)>>>(stats, (int)N, splits, (double)P, (int)C,
+  bn_bwd_finalize_kernel<<<(unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream)>>>(stats, (int)N, splits, (double)P, (int)C,
                                                                             (int)Cp, gamma, mean, rstd, train, coef,
                                                                             dgamma, dbeta);
   X3D_LAUNCH_CHECK();
@@ -582,7 +593,7 @@ extern "C" int x3d_swish_gate_bwd_reduce(const void* dv, const void* a2, const f
   X3D_DISPATCH_DTYPE(dt, {
     RowGeom g = make_row_geom<T>(N, P, Cp);
     dim3 grid(g.chunks, (unsigned)N);
-    size_t smem = Cp * 2 * sizeof(float);
+    size_t smem = (size_t)g.rows * Cp * 2 * sizeof(float);
     if (gate)
       swish_gate_bwd_reduce_kernel<T, true><<<grid, g.threads, smem, as_stream(stream)>>>(
           (const T*)dv, (const T*)a2, scale, shift, splits, gate, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
@@ -656,10 +667,12 @@ __global__ void se_bn_bwd_coef_kernel(const double* __restrict__ fwd_stats, cons
                                       const float* __restrict__ gate /*nullable*/, const float* __restrict__ work,
                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
                                       float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Cp) return;
+  // one thread per (split, channel)
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= splits * Cp) return;
+  const int b = idx / Cp, c = idx % Cp;
   if (c >= C) {
-    for (int n = 0; n < N; ++n) {
+    for (int n = b; n < N; n += splits) {
       float* e = coef + ((int64_t)n * Cp + c) * 3;
       e[0] = e[1] = e[2] = 0.f;
     }
@@ -667,36 +680,38 @@ __global__ void se_bn_bwd_coef_kernel(const double* __restrict__ fwd_stats, cons
   }
   const double gm = gamma[c];
   const double m = (double)(N / splits) * P;
-  double dgam = 0.0, dbet = 0.0;
-  for (int b = 0; b < splits; ++b) {
-    double s1 = 0.0, s2 = 0.0;   // sum du, sum du*a2 over the split
+  double s1 = 0.0, s2 = 0.0;   // sum du, sum du*a2 over the split (du = dz*gate + dp/P)
+  if (gate) {
+#pragma unroll 4
     for (int n = b; n < N; n += splits) {
-      const double g = gate ? (double)gate[(int64_t)n * Cp + c] : 1.0;
-      const double dpP = gate ? (double)work[(int64_t)n * Cp + c] : 0.0;
-      s1 += g * bwd_stats[((int64_t)n * Cp + c) * 2 + 0] + dpP * P;
-      s2 += g * bwd_stats[((int64_t)n * Cp + c) * 2 + 1] + dpP * fwd_stats[((int64_t)n * Cp + c) * 2 + 0];
+      const int64_t o = (int64_t)n * Cp + c;
+      const double g = gate[o], dpP = work[o];
+      const double2 bs = __ldg(reinterpret_cast<const double2*>(bwd_stats) + o);
+      s1 += g * bs.x + dpP * P;
+      s2 += g * bs.y + dpP * __ldg(fwd_stats + o * 2);
     }
-    const double mu = mean[b * Cp + c], r = rstd[b * Cp + c];
-    const double sxh = (s2 - mu * s1) * r;
-    dgam += sxh;
-    dbet += s1;
-    double A = gm * r, B = 0.0, Cc = 0.0;
-    if (train) {
-      const double m1 = s1 / m, m2 = sxh / m;
-      B = -gm * r * r * m2;
-      Cc = gm * r * (-m1 + mu * r * m2);
-    }
-    for (int n = b; n < N; n += splits) {
-      const double g = gate ? (double)gate[(int64_t)n * Cp + c] : 1.0;
-      const double dpP = gate ? (double)work[(int64_t)n * Cp + c] : 0.0;
-      float* e = coef + ((int64_t)n * Cp + c) * 3;
-      e[0] = (float)(A * g);
-      e[1] = (float)B;
-      e[2] = (float)(Cc + A * dpP);
-    }
+  } else {
+    sum_split(bwd_stats, N, splits, b, c, Cp, s1, s2);
   }
-  if (dgamma) dgamma[c] += (float)dgam;
-  if (dbeta) dbeta[c] += (float)dbet;
+  const double mu = mean[idx], r = rstd[idx];
+  const double sxh = (s2 - mu * s1) * r;
+  double A = gm * r, B = 0.0, Cc = 0.0;
+  if (train) {
+    const double m1 = s1 / m, m2 = sxh / m;
+    B = -gm * r * r * m2;
+    Cc = gm * r * (-m1 + mu * r * m2);
+  }
+  for (int n = b; n < N; n += splits) {
+    const int64_t o = (int64_t)n * Cp + c;
+    const double g = gate ? (double)gate[o] : 1.0;
+    const double dpP = gate ? (double)work[o] : 0.0;
+    float* e = coef + o * 3;
+    e[0] = (float)(A * g);
+    e[1] = (float)B;
+    e[2] = (float)(Cc + A * dpP);
+  }
+  if (dgamma) atomicAdd(&dgamma[c], (float)sxh);
+  if (dbeta) atomicAdd(&dbeta[c], (float)s1);
 }
 
 extern "C" int x3d_se_bn_bwd(const double* fwd_stats, const double* bwd_stats, int64_t N, int splits, int64_t P,
@@ -713,7 +728,7 @@ extern "C" int x3d_se_bn_bwd(const double* fwd_stats, const double* bwd_stats, i
                                                                        gate, dW1, db1, dW2, db2, work);
     X3D_LAUNCH_CHECK();
   }
-  se_bn_bwd_coef_kernel<<<(unsigned)cdiv(Cp, 64), 64, 0, as_stream(stream)>>>(fwd_stats, bwd_stats, (int)N, splits,
+  se_bn_bwd_coef_kernel<<<(unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream)>>>(fwd_stats, bwd_stats, (int)N, splits,
                                                                            (double)P, (int)C, (int)Cp, gamma, mean, rstd,
                                                                            train, gate, work, dgamma, dbeta, coef);
   X3D_LAUNCH_CHECK();
@@ -875,7 +890,7 @@ extern "C" int x3d_bn_relu_pool_bwd_reduce(const void* a5, const float* scale, c
   X3D_DISPATCH_DTYPE(dt, {
     RowGeom g = make_row_geom<T>(R, Pp, Cp);
     dim3 grid(g.chunks, (unsigned)R);
-    bn_relu_pool_bwd_kernel<T, false><<<grid, g.threads, Cp * 2 * sizeof(float), as_stream(stream)>>>(
+    bn_relu_pool_bwd_kernel<T, false><<<grid, g.threads, (size_t)g.rows * Cp * 2 * sizeof(float), as_stream(stream)>>>(
         (const T*)a5, scale, shift, splits, dpooled, stats, nullptr, nullptr, pool_t ? 1 : (int)T_, Pp, (int)C, (int)Cp,
         g.cv, g.rows, g.chunk);
   });
@@ -986,33 +1001,28 @@ __global__ void skinny_gemm_kcontig_kernel(const float* __restrict__ A, int64_t 
     }
   }
 }
-// (b) B j-contiguous (sbj == 1): one thread per output column, loop over K (A broadcast through L1)
+// (b) B j-contiguous (sbj == 1): thread = output column, K split over blockIdx.y, fp32 atomics into C
+//     (C zeroed by the launcher unless accumulating; no bias / relu / mul on this path)
 template <int MR>
 __global__ void skinny_gemm_jcontig_kernel(const float* __restrict__ A, int64_t sai, int64_t sak,
                                            const float* __restrict__ B, int64_t sbk, float* __restrict__ C, int64_t ldc,
-                                           int M, int Nn, int K, const float* __restrict__ bias, int relu,
-                                           const float* __restrict__ mul, int accumulate) {
+                                           int M, int Nn, int K, int kchunk) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Nn) return;
+  const int k0 = blockIdx.y * kchunk;
+  const int k1 = k0 + kchunk < K ? k0 + kchunk : K;
   float acc[MR];
 #pragma unroll
   for (int i = 0; i < MR; ++i) acc[i] = 0.f;
-  for (int k = 0; k < K; ++k) {
+  for (int k = k0; k < k1; ++k) {
     const float b = B[(int64_t)k * sbk + j];
 #pragma unroll
     for (int i = 0; i < MR; ++i)
-      if (i < M) acc[i] = fmaf(A[(int64_t)i * sai + (int64_t)k * sak], b, acc[i]);
+      if (i < M) acc[i] = fmaf(__ldg(&A[(int64_t)i * sai + (int64_t)k * sak]), b, acc[i]);
   }
 #pragma unroll
-  for (int i = 0; i < MR; ++i) {
-    if (i < M) {
-      float v = acc[i] + (bias ? bias[j] : 0.f);
-      if (relu) v = fmaxf(v, 0.f);
-      if (mul) v *= mul[(int64_t)i * Nn + j];
-      float* dst = &C[(int64_t)i * ldc + j];
-      *dst = accumulate ? (*dst + v) : v;
-    }
-  }
+  for (int i = 0; i < MR; ++i)
+    if (i < M && acc[i] != 0.f) atomicAdd(&C[(int64_t)i * ldc + j], acc[i]);
 }
 
 extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
@@ -1025,9 +1035,15 @@ extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const fl
       A, sai, sak, B, sbj, C, ldc, (int)M, (int)Nn, (int)K, bias, relu, mul, accumulate)
     if (M <= 8) SK_(8); else if (M <= 16) SK_(16); else SK_(32);
 #undef SK_
-  } else if (M <= 32 && sbj == 1) {
-#define SJ_(MR) skinny_gemm_jcontig_kernel<MR><<<(unsigned)cdiv(Nn, 64), 64, 0, as_stream(stream)>>>( \
-      A, sai, sak, B, sbk, C, ldc, (int)M, (int)Nn, (int)K, bias, relu, mul, accumulate)
+  } else if (M <= 32 && sbj == 1 && !bias && !relu && !mul && ldc == Nn) {
+    if (!accumulate) {
+      cudaError_t e = cudaMemsetAsync(C, 0, sizeof(float) * M * Nn, as_stream(stream));
+      if (e != cudaSuccess) { set_error("x3d_small_gemm: memset failed"); return (int)e; }
+    }
+    const int kchunk = 64;
+    dim3 grid((unsigned)cdiv(Nn, 64), (unsigned)cdiv(K, kchunk));
+#define SJ_(MR) skinny_gemm_jcontig_kernel<MR><<<grid, 64, 0, as_stream(stream)>>>( \
+      A, sai, sak, B, sbk, C, ldc, (int)M, (int)Nn, (int)K, kchunk)
     if (M <= 8) SJ_(8); else if (M <= 16) SJ_(16); else SJ_(32);
 #undef SJ_
   } else {
