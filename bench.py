@@ -180,9 +180,16 @@ def main():
     torch.manual_seed(0)
     model = X.generate_model(args.version, n_classes=args.classes, base_bn_splits=args.bn_splits, dropout=0.5)
     model = model.to(dev).set_compute_dtype(dtype).train()
-    net = DistributedX3D(model) if world > 1 else model
     use_graph = not args.no_graph
-    opt = FusedSGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-5, capturable=use_graph)
+    # eager: bucketed allreduce launched from inside backward (parallel.DistributedX3D); graph: forward+backward are
+    # replayed as one CUDA graph, then ONE allreduce of the flat gradient buffer + the one-kernel SGD run eagerly
+    net = DistributedX3D(model) if (world > 1 and not use_graph) else model
+    if world > 1 and use_graph:
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=0)
+    opt = FusedSGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-5, capturable=use_graph and world == 1)
+    if world > 1 and use_graph:
+        opt.grad_scale = 1.0 / world
     crit = torch.nn.CrossEntropyLoss()
 
     B, T, S = args.batch, args.frames, args.crop
@@ -205,7 +212,8 @@ def main():
     if use_graph:
         # one CUDA graph for the whole step (forward, CE, backward, allreduce, SGD) -- x3d_multigrid_b200.graphs
         from x3d_multigrid_b200.graphs import GraphedTrainStep
-        graphed = GraphedTrainStep(net, opt, crit, dev_x[0], dev_y[0])
+        reduce_fn = (lambda: dist.all_reduce(model.engine().gflat)) if world > 1 else None
+        graphed = GraphedTrainStep(net, opt, crit, dev_x[0], dev_y[0], reduce_fn=reduce_fn)
         train_step = graphed
     else:
         train_step = eager_step

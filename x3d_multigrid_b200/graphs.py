@@ -8,15 +8,20 @@ between 2-3 shapes inside a long cycle: keep one ``GraphedTrainStep`` per (B, T,
     loss = step(clip, labels)          # copies into the static buffers (async), replays, returns the loss tensor
 
 ``optimizer`` should be ``optim.FusedSGD(..., capturable=True)`` so that LR changes reach the graph
-(call ``optimizer.sync_hyper()`` after editing ``param_groups``)."""
+(call ``optimizer.sync_hyper()`` after editing ``param_groups``).
+
+Data parallel: pass ``reduce_fn`` (e.g. ``lambda: dist.all_reduce(model.engine().gflat)``).  The graph then holds
+forward + backward only; the gradient allreduce (one NCCL call on the flat 15 MB buffer, ~0.1 ms over NVLink) and
+the one-kernel optimizer step run eagerly after the replay -- NCCL work is never captured."""
 from __future__ import annotations
 
 import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, criterion, example_x, example_y, warmup=3):
+    def __init__(self, model, optimizer, criterion, example_x, example_y, warmup=3, reduce_fn=None):
         self.model, self.opt, self.crit = model, optimizer, criterion
+        self.reduce_fn = reduce_fn
         dev = example_x.device
         self.static_x = torch.empty_like(example_x, device=dev)
         self.static_y = torch.empty_like(example_y, device=dev)
@@ -33,16 +38,24 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph):
-            self.static_loss = self._one_step()
+            self.static_loss = self._one_step(captured=True)
         torch.cuda.synchronize(dev)
 
-    def _one_step(self):
+    def _one_step(self, captured=False):
         self.opt.zero_grad(set_to_none=True)
         logits = self.model(self.static_x)
         loss = self.crit(logits, self.static_y)
         loss.backward()
-        self.opt.step()
+        if self.reduce_fn is None:
+            self.opt.step()
+        elif not captured:
+            self._finish()
         return loss.detach()
+
+    def _finish(self):
+        """eager tail of a data-parallel step: gradient allreduce + optimizer"""
+        self.reduce_fn()
+        self.opt.step()
 
     def __call__(self, x, y):
         if x.shape != self.static_x.shape:
@@ -50,9 +63,13 @@ class GraphedTrainStep:
         self.static_x.copy_(x, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
         self.graph.replay()
+        if self.reduce_fn is not None:
+            self._finish()
         return self.static_loss
 
     def replay(self):
         """replay on whatever currently sits in static_x / static_y (inputs staged by the caller)"""
         self.graph.replay()
+        if self.reduce_fn is not None:
+            self._finish()
         return self.static_loss
