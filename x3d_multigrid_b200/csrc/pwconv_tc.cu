@@ -448,7 +448,7 @@ bool make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, 
 // columns k), D[n][k] accumulates in TMEM over the CTA's chunk of rows, then fp32 red.global.add into dW.
 // =================================================================================================
 constexpr int WG_ROWS = 64;                       // m rows per ring stage (4 MMAs of K = 16)
-constexpr int WG_STAGES = 3;
+constexpr int WG_MAX_STAGES = 8;
 constexpr int WG_BOX_BYTES = WG_ROWS * 128;       // one 64 x 64 bf16 box
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
@@ -470,20 +470,24 @@ struct WgParams {
   int a_boxes, b_boxes_full;   // 64-wide boxes per stage for A (1 or 2 valid) and for a full B part
   int rows_per_cta;
   int tmem_cols;
+  int cpa;           // allow the cp.async loader for operands narrower than 64 columns
+  int stages;        // operand ring depth (3..8)
 };
 
 __global__ void __launch_bounds__(NTHREADS)
 pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
-                   float* __restrict__ dW, const WgParams p) {
+                   const __nv_bfloat16* __restrict__ DY, const __nv_bfloat16* __restrict__ X, float* __restrict__ dW,
+                   const WgParams p) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
-  constexpr int A_BYTES = 2 * WG_BOX_BYTES;                   // 128 columns n
-  const int b_stage_bytes = 4 * WG_BOX_BYTES;                 // up to 256 columns k
+  const int A_BYTES = p.a_boxes * WG_BOX_BYTES;               // 64 or 128 columns n
+  const int b_stage_bytes = p.b_boxes_full * WG_BOX_BYTES;    // up to 256 columns k
   const int stage_bytes = A_BYTES + b_stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + WG_STAGES * stage_bytes);
-  uint64_t* empty_bar = full_bar + WG_STAGES;
-  uint64_t* accum_bar = empty_bar + WG_STAGES;
+  const int S = p.stages;                                     // ring depth (<= WG_MAX_STAGES)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + WG_MAX_STAGES * 0 + S * stage_bytes);
+  uint64_t* empty_bar = full_bar + WG_MAX_STAGES;
+  uint64_t* accum_bar = empty_bar + WG_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -498,13 +502,14 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_const
   int b_boxes = (p.Kp - k0 + 63) / 64;
   const int b_need = (p.NB + 63) / 64;
   if (b_boxes > b_need) b_boxes = b_need;
+  const bool cpa_a = p.cpa && p.Np < 64, cpa_b = p.cpa && p.Kp < 64;
+  const int full_count = (cpa_a || cpa_b) ? 160 + ((cpa_a && cpa_b) ? 0 : 1) : 1;   // 5 producer warps (+ expect_tx)
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapDY) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&mapX) : "memory");
-#pragma unroll
-    for (int s = 0; s < WG_STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], full_count);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
@@ -522,11 +527,90 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if ((cpa_a || cpa_b) && warp != 1) {
+    // narrow operand(s) (< 64 columns, i.e. < 128-byte rows): coalesced cp.async of the contiguous 64-row span
+    // into the SWIZZLE_128B atom layout (see pw_tc_kernel); wide operands still use TMA boxes.  All five
+    // non-MMA warps copy (the epilogue warps are idle until the accumulator is complete); the chunk -> (row,
+    // column) decomposition is the same for every step and is computed once.
+    constexpr int NPROD = 160, MAXQ = 8;
+    const int pl = warp == 0 ? lane : 32 * (warp - 1) + lane;       // 0..159
+    const unsigned char* dyb = reinterpret_cast<const unsigned char*>(DY);
+    const unsigned char* xb = reinterpret_cast<const unsigned char*>(X);
+    const int cpr_a = p.Np >> 3, cpr_b = p.Kp >> 3;
+    const int nA = cpa_a ? WG_ROWS * cpr_a : 0, nB = cpa_b ? WG_ROWS * cpr_b : 0;
+    int q_row[MAXQ], q_src[MAXQ], q_dst[MAXQ];                       // row in the step, byte offsets (src<0: unused)
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) {
+      const int q = pl + i * NPROD;
+      q_row[i] = 0; q_src[i] = -1; q_dst[i] = 0;
+      if (q < nA) {
+        const int r = q / cpr_a, c = q - r * cpr_a;
+        q_row[i] = r; q_src[i] = q * 16; q_dst[i] = r * 128 + ((c ^ (r & 7)) << 4);
+      } else if (q < nA + nB) {
+        const int qq = q - nA;
+        const int r = qq / cpr_b, c = qq - r * cpr_b;
+        q_row[i] = r; q_src[i] = qq * 16 + (1 << 30); q_dst[i] = A_BYTES + r * 128 + ((c ^ (r & 7)) << 4);
+      }
+    }
+    const int D = S - 2 > 6 ? 6 : S - 2;
+    for (int it = 0; it < nsteps; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      unsigned char* st = base + s * stage_bytes;
+      const int64_t m = row0 + (int64_t)it * WG_ROWS;
+      const int rows = (int)((row1 - m < WG_ROWS) ? row1 - m : WG_ROWS);
+      if (pl == 0 && !(cpa_a && cpa_b)) {
+        mbar_expect_tx(&full_bar[s], (uint32_t)(((cpa_a ? 0 : a_boxes) + (cpa_b ? 0 : b_boxes)) * WG_BOX_BYTES));
+        if (!cpa_a)
+          for (int j = 0; j < a_boxes; ++j) tma_load_2d(st + j * WG_BOX_BYTES, &mapDY, &full_bar[s], n0 + 64 * j, (int)m);
+        if (!cpa_b)
+          for (int j = 0; j < b_boxes; ++j)
+            tma_load_2d(st + A_BYTES + j * WG_BOX_BYTES, &mapX, &full_bar[s], k0 + 64 * j, (int)m);
+      }
+      const unsigned char* srcA = dyb + m * p.Np * 2;
+      const unsigned char* srcB = xb + m * p.Kp * 2;
+      const uint32_t dst0 = smem_u32(st);
+#pragma unroll
+      for (int i = 0; i < MAXQ; ++i) {
+        if (q_src[i] >= 0) {
+          const bool isb = q_src[i] >= (1 << 30);
+          const bool ok = q_row[i] < rows;
+          const unsigned char* src = (isb ? srcB + (q_src[i] - (1 << 30)) : srcA + q_src[i]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst0 + q_dst[i]),
+                       "l"(ok ? src : srcA), "r"(ok ? 16 : 0)
+                       : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+      // keep D = S-2 younger groups in flight: publish the step whose copies are now guaranteed complete
+      if (it >= D) {
+        switch (D) {
+          case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
+          case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
+          case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
+          case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
+          case 5: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
+          default: asm volatile("cp.async.wait_group 6;\n" ::: "memory"); break;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[(it - D) % S])) : "memory");
+      }
+    }
+    if (nsteps > 0) {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      for (int j = (nsteps > D ? nsteps - D : 0); j < nsteps; ++j)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[j % S])) : "memory");
+    }
+  }
   if (warp == 0) {
-    if (lane == 0) {
+    if (cpa_a || cpa_b) {
+      // (copied above together with the epilogue warps)
+    } else if (lane == 0) {
       for (int it = 0; it < nsteps; ++it) {
-        const int s = it % WG_STAGES;
-        const uint32_t ph = (it / WG_STAGES) & 1;
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], (uint32_t)((a_boxes + b_boxes) * WG_BOX_BYTES));
         unsigned char* st = base + s * stage_bytes;
@@ -540,8 +624,8 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_const
     if (lane == 0) {
       const uint32_t idesc = make_idesc_mn(p.NB);
       for (int it = 0; it < nsteps; ++it) {
-        const int s = it % WG_STAGES;
-        const uint32_t ph = (it / WG_STAGES) & 1;
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(base + s * stage_bytes), b_addr = a_addr + A_BYTES;
@@ -600,10 +684,24 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
   p.NB = (int)(((Kp + kparts - 1) / kparts + 15) / 16 * 16);
   if (p.NB > 256) return 0;
   p.tmem_cols = p.NB <= 32 ? 32 : p.NB <= 64 ? 64 : p.NB <= 128 ? 128 : 256;
-  p.a_boxes = 2; p.b_boxes_full = (p.NB + 63) / 64;
+  p.a_boxes = Np > 64 ? 2 : 1; p.b_boxes_full = (p.NB + 63) / 64;
   const int ntiles = (int)((Np + 127) / 128);
   const int kz = (int)((Kp + p.NB - 1) / p.NB);
-  int64_t msplit = (2 * kNumSMs + ntiles * kz - 1) / (ntiles * kz);
+  // Every CTA ends with an fp32 red per element of its dW tile and same-address reds serialise in L2 (~40 ns
+  // each): few M-splits for small M (1 CTA per SM, deep ring), up to 4 CTAs per SM only when M is huge and the
+  // per-step producer overhead has to be hidden by co-resident CTAs.
+  const int stage_kb = 8 * (p.a_boxes + p.b_boxes_full);
+  static const int ctas_env = getenv("X3D_WG_CTAS") ? atoi(getenv("X3D_WG_CTAS")) : 0;   // tuning knob
+  int64_t target = ctas_env > 0 ? ctas_env : M / 2700;
+  if (target < kNumSMs) target = kNumSMs;
+  if (target > 4 * kNumSMs) target = 4 * kNumSMs;
+  int per_sm = (int)((target + kNumSMs - 1) / kNumSMs);
+  while (per_sm > 1 && per_sm * 3 * stage_kb > 200) --per_sm;
+  if (target > (int64_t)per_sm * kNumSMs) target = (int64_t)per_sm * kNumSMs;
+  p.stages = (200 / per_sm) / stage_kb;
+  if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
+  if (p.stages < 3) p.stages = 3;
+  int64_t msplit = (target + ntiles * kz - 1) / (ntiles * kz);
   const int64_t max_split = (M + 511) / 512;
   if (msplit > max_split) msplit = max_split;
   // every CTA ends with one fp32 red per element of its dW tile: keep the total under ~2M reds
@@ -616,14 +714,16 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
   CUtensorMap mapDY, mapX;
   if (!make_map_2d(&mapDY, dy, M, Np, WG_ROWS)) return 0;
   if (!make_map_2d(&mapX, x, M, Kp, WG_ROWS)) return 0;
-  const size_t smem = 1024 + (size_t)WG_STAGES * 6 * WG_BOX_BYTES + (2 * WG_STAGES + 1) * 8 + 16;
+  const size_t smem = 1024 + (size_t)p.stages * (p.a_boxes + p.b_boxes_full) * WG_BOX_BYTES + (2 * WG_MAX_STAGES + 1) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr_done = true;
   }
   dim3 grid((unsigned)msplit, (unsigned)ntiles, (unsigned)kz);
-  pw_wgrad_tc_kernel<<<grid, NTHREADS, smem, stream>>>(mapDY, mapX, dw, p);
+  static const bool no_cpa = getenv("X3D_TC_NOCPA") != nullptr;
+  p.cpa = no_cpa ? 0 : 1;
+  pw_wgrad_tc_kernel<<<grid, NTHREADS, smem, stream>>>(mapDY, mapX, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, p);
   *handled = true;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -88,6 +88,7 @@ extern "C" int x3d_stem_conv_s_fwd(const float* x, const float* w, void* y, int6
 
 // wgrad: dw[co][tap] += sum_p dy[p][co] * xcol[p][tap].  Block: 256 threads = 32 taps x 8 channel groups.
 constexpr int SW_POS = 128;
+constexpr long long kNoPos = (long long)0x8000000000000000ull;   // sentinel: position beyond the tensor
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                           float* __restrict__ dw, int Ci, int T_, int H, int W,
@@ -96,6 +97,8 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   extern __shared__ float sm[];
   float* Xs = sm;                   // [SW_POS][32]
   float* Ds = sm + SW_POS * 32;     // [SW_POS][Cop]
+  long long* s_base = reinterpret_cast<long long*>(Ds + SW_POS * Cop);   // [SW_POS]
+  int* s_flag = reinterpret_cast<int*>(s_base + SW_POS);                   // [SW_POS]
   const int taps = Ci * 9;
   // register tile: a thread owns 3 taps x 8 channels and every `nslice`-th position of the tile
   const int ncg = Cop / 8;                      // channel groups
@@ -112,28 +115,54 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   const int64_t pb = (int64_t)blockIdx.x * pos_per_block;
   const int64_t pe = (pb + pos_per_block < total) ? pb + pos_per_block : total;
   for (int64_t ps = pb; ps < pe; ps += SW_POS) {
-    // im2col tile
-    for (int i = threadIdx.x; i < SW_POS * 32; i += 256) {
-      const int pp = i / 32, tp = i % 32;
-      const int64_t p = ps + pp;
-      float v = 0.f;
-      if (p < pe && tp < taps) {
+    // per-position decode once (n, t, ho, wo -> offset of tap (ci=0, j=0, k=0) and border flags)
+    if (threadIdx.x < SW_POS) {
+      const int64_t p = ps + threadIdx.x;
+      long long base = kNoPos;
+      int flags = 0;
+      if (p < pe) {
         const int wo = (int)(p % Wo);
         int64_t r = p / Wo;
         const int ho = (int)(r % Ho);
         r /= Ho;
         const int t = (int)(r % T_);
         const int n = (int)(r / T_);
+        base = ((((int64_t)n * Ci) * T_ + t) * H + (2 * ho - 1)) * (int64_t)W + (2 * wo - 1);
+        // bit j: row 2ho+j-1 inside the image; bit 3+k: column 2wo+k-1 inside the image
+        for (int j = 0; j < 3; ++j) flags |= (2 * ho + j - 1 >= 0 && 2 * ho + j - 1 < H) ? (1 << j) : 0;
+        for (int k = 0; k < 3; ++k) flags |= (2 * wo + k - 1 >= 0 && 2 * wo + k - 1 < W) ? (8 << k) : 0;
+      }
+      s_base[threadIdx.x] = base;
+      s_flag[threadIdx.x] = flags;
+    }
+    __syncthreads();
+    // im2col tile: item = (position, tap)
+    const int64_t chan_stride = (int64_t)T_ * H * W;
+    for (int i = threadIdx.x; i < SW_POS * 32; i += 256) {
+      const int pp = i / 32, tp = i % 32;
+      float v = 0.f;
+      const long long base = s_base[pp];
+      if (base != kNoPos && tp < taps) {
         const int ci = tp / 9, j = (tp % 9) / 3, k = tp % 3;
-        const int hh = 2 * ho + j - 1, ww = 2 * wo + k - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(&x[((((int64_t)n * Ci + ci) * T_ + t) * H + hh) * W + ww]);
+        const int fl = s_flag[pp];
+        if ((fl >> j) & (fl >> (3 + k)) & 1) v = __ldg(&x[base + ci * chan_stride + (int64_t)j * W + k]);
       }
       Xs[i] = v;
     }
-    for (int i = threadIdx.x; i < SW_POS * Cop; i += 256) {
-      const int pp = i / Cop;
-      const int64_t p = ps + pp;
-      Ds[i] = (p < pe) ? to_float<T>(dy[p * Cop + (i % Cop)]) : 0.f;
+    {
+      // dy tile: 16-byte vector loads (Cop % 8 == 0), converted to fp32
+      constexpr int VEC = Vec<T>::N;
+      const int vpr = Cop / VEC;
+      for (int i = threadIdx.x; i < SW_POS * vpr; i += 256) {
+        const int pp = i / vpr, cvq = (i % vpr) * VEC;
+        const int64_t p = ps + pp;
+        float v[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) v[q] = 0.f;
+        if (p < pe) load_vec<T>(dy + p * Cop + cvq, v);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) Ds[pp * Cop + cvq + q] = v[q];
+      }
     }
     __syncthreads();
     if (active) {
@@ -183,7 +212,7 @@ extern "C" int x3d_stem_conv_s_wgrad(const float* x, const void* dy, float* dw, 
   int64_t blocks = 4 * kNumSMs;
   int64_t ppb = cdiv(cdiv(total, blocks), SW_POS) * SW_POS;
   blocks = cdiv(total, ppb);
-  size_t smem = (size_t)(SW_POS * 32 + SW_POS * Cop) * sizeof(float);
+  size_t smem = (size_t)(SW_POS * 32 + SW_POS * Cop) * sizeof(float) + SW_POS * (sizeof(long long) + sizeof(int));
   X3D_DISPATCH_DTYPE(dt, (stem_wgrad_kernel<T><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
                              x, (const T*)dy, dw, (int)Ci, (int)T_, (int)H, (int)W, Ho, Wo, (int)Co, (int)Cop, total, ppb)));
   X3D_LAUNCH_CHECK();
