@@ -249,11 +249,14 @@ def main():
     if use_graph:
         # the timed region replays a CUDA graph (no per-kernel host calls): the SAME kernels on the same shapes are
         # timed here, in this process, with CUDA events around each depthwise call of 3 eager steps
+        # (weight-gradient kernels back on the main stream, so that every kernel is timed running alone)
         L.prof_names, L.prof_records = set(prof_names), []
         l0 = L.launch_count()
+        side, model.engine().side = model.engine().side, None
         for i in range(3):
             eager_step(dev_x[i % n_host], dev_y[i % n_host])
         torch.cuda.synchronize()
+        model.engine().side = side
         launches = (L.launch_count() - l0) // 3 * args.steps       # kernels per step x replayed steps
         roofline_note = ('timed region = CUDA-graph replays; kernel times from per-call CUDA events over 3 eager steps '
                          'run right after it in the same process')
@@ -341,9 +344,11 @@ def main():
     if args.kernel_table:
         # two extra (untimed) EAGER steps with EVERY C-ABI call bracketed by events: where the step goes
         L.prof_names, L.prof_records = set(L.fn), []
+        side, model.engine().side = model.engine().side, None
         for i in range(2):
             eager_step(dev_x[i % n_host], dev_y[i % n_host])
         torch.cuda.synchronize()
+        model.engine().side = side
         full = {}
         for name, a, ev0, ev1 in L.prof_records:
             d = full.setdefault(name, {'launches': 0, 'ms_total': 0.0})

@@ -16,6 +16,7 @@ are still running backward).
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -101,6 +102,7 @@ class Engine:
         self._sig = None
         self.arena_f: Optional[Arena] = None
         self.arena_b: Optional[Arena] = None
+        self.side = None
         self.grad_hook: Optional[Callable[[int], None]] = None   # called after each bucket's grads are final
 
     # ------------------------------------------------------------------ parameter tables
@@ -122,6 +124,9 @@ class Engine:
             if p.device != device or p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError('all parameters must be contiguous fp32 tensors on the input device')
         self.arena_f, self.arena_b = Arena(device), Arena(device)
+        # weight-gradient kernels feed nothing downstream: they run on a side stream, concurrently with the
+        # dgrad / BN chain of the main stream (fills the SMs that the small late-stage kernels leave idle)
+        self.side = torch.cuda.Stream(device) if (device.type == 'cuda' and not os.environ.get('X3D_NO_SIDE')) else None
 
         # ---- flat gradient buffer, bucket order: head+stage4 first ... stem last
         named = dict(m.named_parameters())
@@ -241,6 +246,25 @@ class Engine:
         self.lib.call('x3d_ndhwc_to_ncdhw', _ptr(x), _ptr(out), N, C, Cp, T, H, W, self.dt, self._stream())
         return out
 
+    def _wgrad(self, name, tensors, *args):
+        """launch a weight-gradient kernel on the side stream once everything enqueued so far has run"""
+        main = torch.cuda.current_stream(self.device)
+        if self.side is None:
+            self.lib.call(name, *args, main.cuda_stream)
+            return
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(self.side)
+        with torch.cuda.stream(self.side):
+            self.lib.call(name, *args, self.side.cuda_stream)
+
+    def _join_side(self):
+        if self.side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+
     def pack_weights(self):
         self.lib.call('x3d_pack_params', self.pack_descs.data_ptr(), self.n_pack, self.pack_max, self._stream())
 
@@ -322,13 +346,13 @@ class Engine:
         C0 = m.conv1_s.out_channels
         P = T * H1 * W1
         da_t = self._bn_backward(self.arena_b, 'bn1', bn0, dx0, x0, a_t, N, P, C0, C0p, dx0)
-        lib.call('x3d_dwconv_wgrad', _ptr(a_s), _ptr(da_t), self.g('conv1_t.weight'), N, T, H1, W1, C0, C0p,
-                 5, 1, 1, 1, None, None, 1, 0, self.dt, st)
+        self._wgrad('x3d_dwconv_wgrad', (a_s, da_t), _ptr(a_s), _ptr(da_t), self.g('conv1_t.weight'), N, T, H1, W1, C0,
+                    C0p, 5, 1, 1, 1, None, None, 1, 0, self.dt)
         da_s = self._act(N, T, H1, W1, C0p)
         lib.call('x3d_dwconv_dgrad', _ptr(da_t), self.pk('conv1_t.d'), _ptr(da_s), N, T, H1, W1, C0p, 5, 1, 1, 1,
                  None, None, None, 1, None, self.dt, st)
-        lib.call('x3d_stem_conv_s_wgrad', _ptr(x), _ptr(da_s), self.g('conv1_s.weight'), N, Ci, T, H, W, C0, C0p,
-                 self.dt, st)
+        self._wgrad('x3d_stem_conv_s_wgrad', (x, da_s), _ptr(x), _ptr(da_s), self.g('conv1_s.weight'), N, Ci, T, H, W,
+                    C0, C0p, self.dt)
 
     # ------------------------------------------------------------------ bottleneck
     def block_fwd(self, blk, x, geom, training, save_list):
@@ -402,8 +426,8 @@ class Engine:
         da3 = self._act(N, T, Ho, Wo, Cop)
         self._bn_backward(ab, pre + '.bn3', bn3, dout, out, a3, N, P_out, Co, Cop, da3)
         # ---- conv3
-        lib.call('x3d_pwconv_wgrad', _ptr(v), _ptr(da3), self.g(pre + '.conv3.weight'), N, T, Ho, Wo, Cm, Cmp, Co,
-                 Cop, 1, dt, st)
+        self._wgrad('x3d_pwconv_wgrad', (v, da3), _ptr(v), _ptr(da3), self.g(pre + '.conv3.weight'), N, T, Ho, Wo, Cm,
+                    Cmp, Co, Cop, 1, dt)
         dv = self._act(N, T, Ho, Wo, Cmp)
         lib.call('x3d_pwconv_dgrad', _ptr(da3), self.pk(pre + '.conv3.t'), _ptr(dv), N, T, Ho, Wo, Cmp, Cop, 1, 0,
                  dt, st)
@@ -430,8 +454,8 @@ class Engine:
         lib.call('x3d_swish_gate_bwd_apply', _ptr(dv), _ptr(a2), _ptr(bn2.scale), _ptr(bn2.shift), bn2.splits,
                  _ptr(gate), _ptr(coef2), _ptr(da2), N, P_out, Cmp, dt, st)
         # ---- depthwise conv2
-        lib.call('x3d_dwconv_wgrad', _ptr(a1), _ptr(da2), self.g(pre + '.conv2.weight'), N, T, H, W, Cm, Cmp, 3, 3, 3,
-                 s, _ptr(bn1.scale), _ptr(bn1.shift), bn1.splits, 1, dt, st)
+        self._wgrad('x3d_dwconv_wgrad', (a1, da2, bn1.scale), _ptr(a1), _ptr(da2), self.g(pre + '.conv2.weight'), N, T,
+                    H, W, Cm, Cmp, 3, 3, 3, s, _ptr(bn1.scale), _ptr(bn1.shift), bn1.splits, 1, dt)
         d1 = self._act(N, T, H, W, Cmp)
         bst1 = self._stats(ab, N, Cmp)
         lib.call('x3d_dwconv_dgrad', _ptr(da2), self.pk(pre + '.conv2.d'), _ptr(d1), N, T, H, W, Cmp, 3, 3, 3, s,
@@ -445,8 +469,8 @@ class Engine:
         da1 = d1
         lib.call('x3d_bn_bwd_apply', _ptr(d1), None, _ptr(a1), _ptr(coef1), bn1.splits, _ptr(da1), N, P_in, Cmp, dt, st)
         # ---- conv1
-        lib.call('x3d_pwconv_wgrad', _ptr(x), _ptr(da1), self.g(pre + '.conv1.weight'), N, T, H, W, Cin, Cinp, Cm, Cmp,
-                 1, dt, st)
+        self._wgrad('x3d_pwconv_wgrad', (x, da1), _ptr(x), _ptr(da1), self.g(pre + '.conv1.weight'), N, T, H, W, Cin,
+                    Cinp, Cm, Cmp, 1, dt)
         dx = None
         if need_dx:
             dx = self._act(N, T, H, W, Cinp)
@@ -456,8 +480,8 @@ class Engine:
         if blk.downsample is not None:
             dad = self._act(N, T, Ho, Wo, Cop)
             self._bn_backward(ab, pre + '.downsample.1', bnd, dout, out, ad, N, P_out, Co, Cop, dad)
-            lib.call('x3d_pwconv_wgrad', _ptr(x), _ptr(dad), self.g(pre + '.downsample.0.weight'), N, T, H, W, Cin,
-                     Cinp, Co, Cop, s, dt, st)
+            self._wgrad('x3d_pwconv_wgrad', (x, dad), _ptr(x), _ptr(dad), self.g(pre + '.downsample.0.weight'), N, T, H,
+                        W, Cin, Cinp, Co, Cop, s, dt)
             if need_dx:
                 lib.call('x3d_pwconv_dgrad', _ptr(dad), self.pk(pre + '.downsample.0.t'), _ptr(dx), N, T, H, W, Cinp,
                          Cop, s, 1, dt, st)
@@ -537,8 +561,8 @@ class Engine:
         lib.call('x3d_bn_relu_pool_bwd_apply', _ptr(a5), _ptr(bn5.scale), _ptr(bn5.shift), bn5.splits, _ptr(dpooled),
                  _ptr(coef5), _ptr(da5), N, T, H * W, pool_t, C5, C5p, dt, st)
         # conv5
-        lib.call('x3d_pwconv_wgrad', _ptr(xL), _ptr(da5), self.g('conv5.weight'), N, T, H, W, C5in, C5inp, C5, C5p, 1,
-                 dt, st)
+        self._wgrad('x3d_pwconv_wgrad', (xL, da5), _ptr(xL), _ptr(da5), self.g('conv5.weight'), N, T, H, W, C5in, C5inp,
+                    C5, C5p, 1, dt)
         dxL = self._act(N, T, H, W, C5inp)
         lib.call('x3d_pwconv_dgrad', _ptr(da5), self.pk('conv5.t'), _ptr(dxL), N, T, H, W, C5inp, C5p, 1, 0, dt, st)
         return dxL
@@ -574,8 +598,10 @@ class Engine:
             blocks[i] = None
             # bucket b (0 = head+stage4, 1 = stage3, 2 = stage2) is final once its first block is done
             if self.grad_hook and (i == 0 or stage_of[i - 1] != stage_of[i]) and stage_of[i] > 1:
+                self._join_side()
                 self.grad_hook(4 - stage_of[i])
         self._stem_bwd(save, d)
+        self._join_side()
         if self.grad_hook:
             self.grad_hook(3)
         return self.param_grads()

@@ -117,6 +117,7 @@ class _BlockFunction(torch.autograd.Function):
         eng.new_grad_buffer()
         d = eng.to_ndhwc(dy.contiguous().float())
         dx = eng.block_bwd(ctx.rec, d, need_dx=True)
+        eng._join_side()
         grads = eng.param_grads()
         out = [g if need else None for g, need in zip(grads, ctx.needs_input_grad[3:])]
         dxo = eng.to_ncdhw(dx, ctx.in_shape[1]) if ctx.needs_input_grad[0] else None
