@@ -177,6 +177,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   uint64_t* b_bar = accum_empty + 2;                            // resident-weights barrier (cp.async path)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);      // [BN][2]
+  float* s_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BN) + 15) & ~(uintptr_t)15);                              // [row groups][ncols][2] partial sums (<= 4 KB)
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n0 = blockIdx.y * BN;
@@ -311,22 +312,41 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int q = warp & 3;                                // TMEM lane quarter this warp may access
     const int et = threadIdx.x - 64;                       // 0..127 among the epilogue threads
     const int rloc = q * 32 + lane;                        // row of the tile owned by this thread
-    // statistics: per-CTA accumulators s_stat[col][2] of the sample `cur_samp`; flushed to global (fp64
-    // atomics) only when the CTA's contiguous tile range moves on to another sample
+    // statistics: every thread keeps register partial sums (sum, sum of squares of 4 columns over its row group)
+    // of the sample `cur_samp`; they are combined through a small scratch array and flushed to global (fp64
+    // atomics) only when the CTA's contiguous tile range moves on to another sample.
+    // thread = (4-column group cq, row group grp): one 8-byte shared load per row feeds packed f32x2 adds / FMAs
+    const int nquad = ncols >> 2;
+    int groups = 128 / nquad;
+    if (groups > 16) groups = 16;
+    const int cq = et % nquad, grp = et / nquad;
+    const bool worker = et < nquad * groups;
+    const int pstride = ncols * 2;                                  // scratch row: [col][sum, sumsq]
+    float2 s1a = make_float2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
     long long cur_samp = -1;
-    auto flush_stats = [&]() {
+    long long samp_lim = 0;                                         // first global row of the next sample
+    auto flush_stats = [&]() {                                      // called by all 128 epilogue threads
       if (cur_samp >= 0) {
-        for (int i = et; i < BN * 2; i += 128) {
-          const int col = i >> 1;
-          const float v = s_stat[i];
-          if (col < ncols && v != 0.f) atomicAdd(&stats[(cur_samp * p.ldc + n0 + col) * 2 + (i & 1)], (double)v);
-          s_stat[i] = 0.f;
+        if (worker) {
+          float4* dst = reinterpret_cast<float4*>(s_part + grp * pstride + cq * 8);
+          dst[0] = make_float4(s1a.x, s2a.x, s1a.y, s2a.y);
+          dst[1] = make_float4(s1b.x, s2b.x, s1b.y, s2b.y);
         }
+        asm volatile("bar.sync 2, 128;\n" ::: "memory");
+        for (int i = et; i < pstride; i += 128) {
+          float v = 0.f;
+          for (int gq = 0; gq < groups; ++gq) v += s_part[gq * pstride + i];
+          if (v != 0.f) atomicAdd(&stats[(cur_samp * p.ldc + n0 + (i >> 1)) * 2 + (i & 1)], (double)v);
+        }
+        asm volatile("bar.sync 2, 128;\n" ::: "memory");             // scratch reusable
+        s1a = s1b = s2a = s2b = make_float2(0.f, 0.f);
       }
     };
-    if (STATS) {
-      for (int i = et; i < BN * 2; i += 128) s_stat[i] = 0.f;
-    }
+    // copy-out: consecutive threads write consecutive 16-byte chunks of the output rows; chunk -> (row, chunk in
+    // row) is advanced incrementally (no division in the loop)
+    const int cpr = ncols >> 3;                              // 16-byte chunks per row
+    const int co_r0 = et / cpr, co_c0 = et - co_r0 * cpr;
+    const int co_dr = 128 / cpr, co_dc = 128 - co_dr * cpr;
     int tcount = 0;
     for (int tm = tile_begin; tm < tile_end; ++tm, ++tcount) {
       const int buf = tcount & 1;
@@ -355,53 +375,47 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&accum_empty[buf])) : "memory");
       }
       asm volatile("bar.sync 1, 128;\n" ::: "memory");     // tile staged in shared memory
-      // coalesced copy-out: consecutive threads write consecutive 16-byte chunks of the output rows
       const int rows_valid = (p.M - m0 < BM) ? p.M - m0 : BM;
-      const int cpr = ncols >> 3;                            // 16-byte chunks per row
-      const int nchunks = rows_valid * cpr;
-      for (int ch = et; ch < ((p.dbg & 1) ? 0 : nchunks); ch += 128) {
-        const int r = ch / cpr, cc = ch - r * cpr;
-        const uint4 v = *reinterpret_cast<const uint4*>(c_s + r * p.cpitch + cc * 8);
-        *reinterpret_cast<uint4*>(C + (int64_t)(m0 + r) * p.ldc + n0 + cc * 8) = v;
+      if (!(p.dbg & 1)) {
+        int r = co_r0, cc = co_c0;
+        while (r < rows_valid) {
+          const uint4 v = *reinterpret_cast<const uint4*>(c_s + r * p.cpitch + cc * 8);
+          *reinterpret_cast<uint4*>(C + (int64_t)(m0 + r) * p.ldc + n0 + cc * 8) = v;
+          r += co_dr;
+          cc += co_dc;
+          if (cc >= cpr) { cc -= cpr; ++r; }
+        }
       }
       if (STATS && !(p.dbg & 2)) {
-        // column sums of the staged (bf16-rounded) tile, one row segment per sample touched by the tile:
-        // thread = (column pair, row group); conflict-free 4-byte shared loads, no shuffles
-        const int npair = ncols >> 1;
-        const int groups = 128 / npair > 0 ? 128 / npair : 1;        // row groups working on a column pair
-        const int cp = et % npair, grp = et / npair;
+        // column sums of the staged (bf16-rounded) tile, one row segment per sample touched by the tile
         int r0 = 0;
         while (r0 < rows_valid) {
-          const long long samp = (long long)(m0 + r0) / p.P_out;
-          long long lim = (samp + 1) * p.P_out - m0;                // first row of the next sample (tile-local)
-          const int r1 = lim < rows_valid ? (int)lim : rows_valid;
-          if (samp != cur_samp) {                                   // uniform across the 128 threads
-            asm volatile("bar.sync 2, 128;\n" ::: "memory");        // everybody's atomics of the old sample landed
+          const long long g0 = (long long)m0 + r0;
+          if (cur_samp < 0 || g0 >= samp_lim) {                     // uniform across the 128 threads
             flush_stats();
-            cur_samp = samp;
-            asm volatile("bar.sync 2, 128;\n" ::: "memory");
+            cur_samp = g0 / p.P_out;
+            samp_lim = (cur_samp + 1) * p.P_out;
           }
-          if (et < npair * groups) {
-            float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f;
+          const long long lim = samp_lim - m0;
+          const int r1 = lim < rows_valid ? (int)lim : rows_valid;
+          if (worker) {
+            const __nv_bfloat16* cp = c_s + 4 * cq;
+#pragma unroll 4
             for (int r = r0 + grp; r < r1; r += groups) {
-              const uint32_t wv = *reinterpret_cast<const uint32_t*>(c_s + r * p.cpitch + 2 * cp);
-              const float a = __uint_as_float(wv << 16), b2 = __uint_as_float(wv & 0xffff0000u);
-              s1x += a; s1y += b2;
-              s2x = fmaf(a, a, s2x); s2y = fmaf(b2, b2, s2y);
+              const uint2 wv = *reinterpret_cast<const uint2*>(cp + r * p.cpitch);
+              const float2 a = make_float2(__uint_as_float(wv.x << 16), __uint_as_float(wv.x & 0xffff0000u));
+              const float2 b2 = make_float2(__uint_as_float(wv.y << 16), __uint_as_float(wv.y & 0xffff0000u));
+              s1a = __fadd2_rn(s1a, a);
+              s1b = __fadd2_rn(s1b, b2);
+              s2a = __ffma2_rn(a, a, s2a);
+              s2b = __ffma2_rn(b2, b2, s2b);
             }
-            atomicAdd(&s_stat[(2 * cp) * 2 + 0], s1x);
-            atomicAdd(&s_stat[(2 * cp) * 2 + 1], s2x);
-            atomicAdd(&s_stat[(2 * cp + 1) * 2 + 0], s1y);
-            atomicAdd(&s_stat[(2 * cp + 1) * 2 + 1], s2y);
           }
           r0 = r1;
         }
       }
     }
-    if (STATS) {
-      asm volatile("bar.sync 2, 128;\n" ::: "memory");
-      flush_stats();
-    }
+    if (STATS) flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -765,7 +779,7 @@ int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, 
   if (!make_map_2d(&mapA, x, M, Kp, BM)) return 0;
   if (!make_map_2d(&mapB, w, Np, Kp, BN)) return 0;
   const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + (size_t)BN * BK * 2) + (size_t)BM * p.cpitch * 2 +
-                      (2 * p.stages + 6) * 8 + 16 + (size_t)2 * BN * 2 * sizeof(float);
+                      (2 * p.stages + 6) * 8 + 16 + (size_t)2 * BN * 2 * sizeof(float) + 4096 + 16;
   // resident CTAs: TMEM (512 columns per SM) and shared memory (227 KB per SM) bound the co-residency
   int per_sm = 512 / p.tmem_cols;
   const int by_smem = (int)((227 * 1024) / (smem + 1024));

@@ -454,7 +454,7 @@ class Engine:
         lib.call('x3d_swish_gate_bwd_apply', _ptr(dv), _ptr(a2), _ptr(bn2.scale), _ptr(bn2.shift), bn2.splits,
                  _ptr(gate), _ptr(coef2), _ptr(da2), N, P_out, Cmp, dt, st)
         # ---- depthwise conv2
-        self._wgrad('x3d_dwconv_wgrad', (a1, da2, bn1.scale), _ptr(a1), _ptr(da2), self.g(pre + '.conv2.weight'), N, T,
+        self._wgrad('x3d_dwconv_wgrad', (a1, da2, bn1.scale, bn1.shift), _ptr(a1), _ptr(da2), self.g(pre + '.conv2.weight'), N, T,
                     H, W, Cm, Cmp, 3, 3, 3, s, _ptr(bn1.scale), _ptr(bn1.shift), bn1.splits, 1, dt)
         d1 = self._act(N, T, H, W, Cmp)
         bst1 = self._stats(ab, N, Cmp)
