@@ -19,10 +19,14 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, criterion, example_x, example_y, warmup=3, reduce_fn=None):
+    def __init__(self, model, optimizer, criterion, example_x, example_y, warmup=3, reduce_fn=None,
+                 preserve_state=False):
         self.model, self.opt, self.crit = model, optimizer, criterion
         self.reduce_fn = reduce_fn
         dev = example_x.device
+        # the warm-up steps below are real training steps on the example batch; with preserve_state the parameters,
+        # BN buffers and momentum buffers are put back afterwards (in place: the graph keeps their addresses)
+        snap = self._snapshot() if preserve_state else None
         self.static_x = torch.empty_like(example_x, device=dev)
         self.static_y = torch.empty_like(example_y, device=dev)
         self.static_x.copy_(example_x)
@@ -40,6 +44,29 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.static_loss = self._one_step(captured=True)
         torch.cuda.synchronize(dev)
+        if snap is not None:
+            self._restore(snap)
+
+    def _snapshot(self):
+        net = getattr(self.model, 'module', self.model)
+        tensors = list(net.parameters()) + list(net.buffers())
+        mom = {id(p): self.opt.state[p]['momentum_buffer'].clone() for p in net.parameters()
+               if 'momentum_buffer' in self.opt.state.get(p, {})}
+        return [t.detach().clone() for t in tensors], mom
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        net = getattr(self.model, 'module', self.model)
+        saved, mom = snap
+        for t, s0 in zip(list(net.parameters()) + list(net.buffers()), saved):
+            t.copy_(s0)
+        for p in net.parameters():
+            st = self.opt.state.get(p, {})
+            if 'momentum_buffer' in st:
+                if id(p) in mom:
+                    st['momentum_buffer'].copy_(mom[id(p)])
+                else:
+                    st['momentum_buffer'].zero_()     # momentum*0 + d == the first-step rule buf = d
 
     def _one_step(self, captured=False):
         self.opt.zero_grad(set_to_none=True)

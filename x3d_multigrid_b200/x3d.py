@@ -45,6 +45,22 @@ class SubBatchNorm3d(nn.Module):
         args['num_features'] = self.num_features * self.num_splits
         self.split_bn = nn.BatchNorm3d(**args)
 
+    def set_split_bn(self, num_splits):
+        """Fresh ``split_bn`` for ``num_splits`` groups (x3d.py:301-302 builds a new BatchNorm3d).  One module per
+        split count is kept and reset in place when it comes back, so that its buffers keep their addresses and
+        CUDA graphs captured for an earlier visit of the same long cycle stay valid."""
+        cache = self.__dict__.setdefault('_split_cache', {})
+        cache.setdefault(self.split_bn.num_features // self.num_features, self.split_bn)
+        bn = cache.get(num_splits)
+        if bn is None:
+            bn = nn.BatchNorm3d(num_features=self.num_features * num_splits, affine=False).to(self.weight.device)
+            cache[num_splits] = bn
+        else:
+            bn.to(self.weight.device)
+            bn.reset_running_stats()
+        bn.train(self.training)
+        self.split_bn = bn
+
     def _get_aggregated_mean_std(self, means, stds, n):
         # x3d.py:27-33 ("std" is a variance there too)
         mean = means.view(n, -1).sum(0) / n
@@ -229,7 +245,7 @@ class ResNet(nn.Module):
         for m in self.modules():
             if isinstance(m, SubBatchNorm3d):
                 m.num_splits = self.base_bn_splits * long_cycle_bn_scale
-                m.split_bn = nn.BatchNorm3d(num_features=m.num_features * m.num_splits, affine=False).to(m.weight.device)
+                m.set_split_bn(m.num_splits)
         return self.base_bn_splits * long_cycle_bn_scale
 
     def aggregate_sub_bn_stats(self):
