@@ -170,12 +170,6 @@ def swish_bwd(x, dy):
     return out[:n].view(x.shape).to(dy.dtype)
 
 
-def _leaf_unavailable(name):
-    raise NotImplementedError(
-        f'{name} is a parameter container on the fused path; call it through Bottleneck / ResNet. '
-        f'(No ATen fallback is provided on purpose.)')
-
-
 def sub_batch_norm(mod, x):
     from . import leaf_ops
     return leaf_ops.sub_batch_norm(mod, x)
