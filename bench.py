@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--bn-splits', type=int, default=2)
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-eager', action='store_true', help='reference arm: skip the informational ATen-on-GPU timing')
     ap.add_argument('--no-graph', action='store_true', help='enqueue every kernel from Python instead of replaying a CUDA graph')
     ap.add_argument('--kernel-table', default='', help='write a per-kernel timing table (JSON) here')
     return ap.parse_args()
@@ -115,6 +116,41 @@ def cpu_reference_rate(args, steps, warmup, batch):
     return batch * len(times) / total, total / len(times), cores
 
 
+def gpu_eager_rate(args, steps=5, warmup=2):
+    """Informational: the same oracle port (plain ATen / cuDNN calls, i.e. what stock PyTorch eager launches for the
+    reference's x3d.py) on cuda:0 at the benchmark's full batch, fp32 and bf16 autocast.  Never the product path."""
+    import torch
+    from oracle import x3d_oracle as O
+    if not torch.cuda.is_available():
+        return None
+    out = {}
+    B = args.batch
+    dev = torch.device('cuda', 0)
+    sd = {k: (v.float() if v.is_floating_point() else v).to(dev)
+          for k, v in O.make_state_dict(args.version, args.classes, args.bn_splits).items()}
+    x = torch.randn(B, 3, args.frames, args.crop, args.crop, device=dev)
+    labels = (torch.arange(B, device=dev).unsqueeze(1) % args.classes)
+    for name, ctx in (('fp32', None), ('bf16_autocast', torch.bfloat16)):
+        try:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for it in range(warmup + steps):
+                if it == warmup:
+                    torch.cuda.synchronize()
+                    e0.record()
+                with torch.autocast('cuda', dtype=ctx, enabled=ctx is not None):
+                    O.loss_and_grads(sd, x, labels, version=args.version, splits=args.bn_splits, training=True,
+                                     conv_impl='aten')
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {'clips_per_s': B * 1e3 / ms, 'ms_per_step': ms}
+        except Exception as ex:       # the oracle is CPU test infrastructure; a device/dtype hiccup is not fatal here
+            out[name] = {'error': f'{type(ex).__name__}: {ex}'[:200]}
+    out['what'] = (f'oracle port of x3d.py as stock ATen/cuDNN eager calls on 1 GPU, batch {B}, fwd+bwd (no optimizer), '
+                   f'CUDA-event timed')
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -130,6 +166,11 @@ def run_reference(args):
                                    f'{args.classes} classes (CPU sample: batch {batch})'},
             'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    if not args.no_gpu_eager:
+        try:
+            line['gpu_eager_torch'] = gpu_eager_rate(args)
+        except Exception as ex:
+            line['gpu_eager_torch'] = {'error': f'{type(ex).__name__}: {ex}'[:200]}
     print(json.dumps(line), flush=True)
 
 
