@@ -184,6 +184,9 @@ PW_CASES = [  # N, K, Nout, T, H, W, stride
     (2, 24, 54, 3, 6, 7, 1),
     (2, 54, 24, 2, 5, 5, 1),
     (2, 24, 48, 3, 7, 9, 2),       # downsample, odd sizes
+    (2, 24, 24, 4, 20, 18, 2),     # downsample: several 128-row tiles of gathered rows (tensor-core path, K < 64)
+    (3, 48, 96, 2, 14, 15, 2),
+    (2, 96, 192, 2, 6, 6, 2),      # K >= 64: strided rows stay on the SIMT kernel
     (3, 192, 432, 2, 4, 4, 1),
     (2, 432, 192, 2, 3, 3, 1),
     (4, 96, 216, 1, 2, 2, 1),      # tiny P: tiles span several samples

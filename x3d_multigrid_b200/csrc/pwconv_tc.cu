@@ -104,6 +104,7 @@ struct TcParams {
   int stages;        // operand ring depth
   int cpitch;        // staging row pitch in elements (BN + 8: conflict-free 16-byte st.shared)
   int cpa;           // 1: A tile copied by cp.async (narrow rows), 0: by TMA
+  int gs, gH, gW, gHo, gWo;   // row gather of a strided 1x1x1 conv: output row (nt,ho,wo) reads input row (nt, gs*ho, gs*wo)
   int dbg;           // profiling experiments (X3D_TC_DBG): 1 = skip copy-out, 2 = skip statistics, 4 = skip staging
   long long P_out;
 };
@@ -177,7 +178,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   uint64_t* b_bar = accum_empty + 2;                            // resident-weights barrier (cp.async path)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);      // [BN][2]
-  float* s_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BN) + 15) & ~(uintptr_t)15);                              // [row groups][ncols][2] partial sums (<= 4 KB)
+  float* s_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BN) + 15) & ~(uintptr_t)15);
+  int* s_rowoff = reinterpret_cast<int*>(s_part + 1024);        // [128] gathered input rows of the current tile                              // [row groups][ncols][2] partial sums (<= 4 KB)
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n0 = blockIdx.y * BN;
@@ -245,12 +247,36 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const int rows = (p.M - m0 < BM) ? p.M - m0 : BM;
         const unsigned char* src0 = Ab + (int64_t)m0 * p.Kp * 2;
         const uint32_t dst0 = smem_u32(a_s + s * a_bytes);
-        for (int ch = lane; ch < BM * cpr; ch += 32) {
-          const int r = ch / cpr, c = ch - r * cpr;
-          const bool ok = r < rows;
-          const unsigned char* src = src0 + (ok ? (int64_t)ch * 16 : 0);
-          const uint32_t dst = dst0 + r * 128 + ((c ^ (r & 7)) << 4);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        if (p.gs > 1) {
+          // strided conv (downsample branch): the tile's rows are gathered; input row index per tile row first
+          __syncwarp();
+          for (int r = lane; r < BM; r += 32) {
+            const int m = m0 + r;
+            const int hw = p.gHo * p.gWo;
+            const int nt = m / hw, rem = m - nt * hw;
+            const int ho = rem / p.gWo, wo = rem - ho * p.gWo;
+            s_rowoff[r] = (nt * p.gH + ho * p.gs) * p.gW + wo * p.gs;     // < 2^31 rows (checked on the host)
+          }
+          __syncwarp();
+          const int dr = 32 / cpr, dc = 32 - dr * cpr;
+          int r = lane / cpr, c = lane - r * cpr;
+          for (; r < BM;) {
+            const bool ok = r < rows;
+            const unsigned char* src = Ab + (ok ? ((int64_t)s_rowoff[r] * p.Kp + c * 8) * 2 : 0);
+            const uint32_t dst = dst0 + r * 128 + ((c ^ (r & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            r += dr;
+            c += dc;
+            if (c >= cpr) { c -= cpr; ++r; }
+          }
+        } else {
+          for (int ch = lane; ch < BM * cpr; ch += 32) {
+            const int r = ch / cpr, c = ch - r * cpr;
+            const bool ok = r < rows;
+            const unsigned char* src = src0 + (ok ? (int64_t)ch * 16 : 0);
+            const uint32_t dst = dst0 + r * 128 + ((c ^ (r & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+          }
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         if (it > 0) {                                            // publish the PREVIOUS tile (its copies are done)
@@ -750,6 +776,7 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
 
 // y[M][Np] = x[M][Kp] * w[Np][Kp]^T  (all bf16, dense rows).  *handled = false -> caller uses the SIMT path.
 int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, int64_t Np, int64_t P_out,
+                  const int* gather /* nullptr | {stride, H, W, Ho, Wo} */,
                   double* stats, cudaStream_t stream, bool* handled) {
   *handled = false;
   static const bool off = getenv("X3D_PW_SIMT") != nullptr;      // A/B switch for tests and profiling
@@ -774,12 +801,18 @@ int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, 
   p.dbg = dbg;
   static const bool no_cpa = getenv("X3D_TC_NOCPA") != nullptr;
   p.cpa = (Kp < BK && !no_cpa) ? 1 : 0;
+  p.gs = 1; p.gH = p.gW = p.gHo = p.gWo = 0;
+  if (gather != nullptr && gather[0] > 1) {
+    if (!p.cpa) return 0;                 // the row gather lives in the cp.async loader (Kp < 64)
+    p.gs = gather[0]; p.gH = gather[1]; p.gW = gather[2]; p.gHo = gather[3]; p.gWo = gather[4];
+    if ((M / ((int64_t)p.gHo * p.gWo)) * p.gH * p.gW >= (1ll << 31)) return 0;
+  }
   p.stages = BN > 128 ? 3 : 2;      // small-N layers: 2 stages so that 2-3 CTAs fit per SM (nk is 1-2 there)
   CUtensorMap mapA, mapB;
   if (!make_map_2d(&mapA, x, M, Kp, BM)) return 0;
   if (!make_map_2d(&mapB, w, Np, Kp, BN)) return 0;
   const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + (size_t)BN * BK * 2) + (size_t)BM * p.cpitch * 2 +
-                      (2 * p.stages + 6) * 8 + 16 + (size_t)2 * BN * 2 * sizeof(float) + 4096 + 16;
+                      (2 * p.stages + 6) * 8 + 16 + (size_t)2 * BN * 2 * sizeof(float) + 4096 + 16 + 512;
   // resident CTAs: TMEM (512 columns per SM) and shared memory (227 KB per SM) bound the co-residency
   int per_sm = 512 / p.tmem_cols;
   const int by_smem = (int)((227 * 1024) / (smem + 1024));
