@@ -37,6 +37,35 @@ void count_launch(int n = 1);
   } while (0)
 
 static inline cudaStream_t as_stream(x3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A training step is ~700 dependent kernels, most of them 3-30 us long: every
+// kernel lets its successor become resident right away (pdl_trigger) and orders itself behind its predecessor
+// with pdl_wait() before it touches global memory, so launch latency and the block-scheduling ramp overlap the
+// predecessor's tail.  (griddepcontrol.wait returns once all prerequisite grids have completed and flushed; both
+// instructions are no-ops for a kernel launched without the attribute.)  X3D_NO_PDL=1 launches the classic way.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_trigger();
+  pdl_wait();
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through cudaGetLastError
+}
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr int kNumSMs = 148;

@@ -33,6 +33,7 @@ __global__ void dw_fwd_direct_kernel(const T* __restrict__ x, const float* __res
                                      DwGeom g, const float* __restrict__ scale, const float* __restrict__ shift,
                                      int splits, double* __restrict__ stats, int64_t P, int cv, int rows,
                                      int64_t chunk) {
+  x3d::pdl_prologue();
   extern __shared__ float s_acc[];
   const int Cp = g.Cp;
   constexpr int VEC = Vec<T>::N;
@@ -111,7 +112,7 @@ static int launch_dw_fwd_direct(const void* x, const float* w, void* y, int64_t 
   dim3 grid(rg.chunks, (unsigned)N);
   size_t smem = stats ? (size_t)rg.rows * g.Cp * 2 * sizeof(float) : 0;
 #define L_(XF, RL, ST)                                                                                          \
-  dw_fwd_direct_kernel<T, KT, KH, KW, XF, RL, ST><<<grid, rg.threads, smem, stream>>>(                          \
+  x3d::launch(dw_fwd_direct_kernel<T, KT, KH, KW, XF, RL, ST>, grid, rg.threads, smem, stream,                           \
       (const T*)x, w, (T*)y, g, scale, shift, splits, stats, P, rg.cv, rg.rows, rg.chunk)
   const bool xf = scale != nullptr;
   if (xf && relu_in && stats) L_(true, true, true);
@@ -160,6 +161,7 @@ __global__ void dw_dgrad_direct_kernel(const T* __restrict__ dy, const float* __
                                        DwGeom g, const T* __restrict__ mask_src, const float* __restrict__ mscale,
                                        const float* __restrict__ mshift, int splits, double* __restrict__ stats,
                                        int64_t P /*input positions*/, int cv, int rows, int64_t chunk) {
+  x3d::pdl_prologue();
   extern __shared__ float s_acc[];
   constexpr int VEC = Vec<T>::N;
   const int Cp = g.Cp;
@@ -253,7 +255,7 @@ extern "C" int x3d_dwconv_dgrad(const void* dy, const float* w_packed, void* dx,
     if (handled) return rc;
   }
 #define L_(KT_, KH_, KW_, MK)                                                                                \
-  dw_dgrad_direct_kernel<T, KT_, KH_, KW_, MK><<<grid, rg.threads, smem, as_stream(stream)>>>(                  \
+  x3d::launch(dw_dgrad_direct_kernel<T, KT_, KH_, KW_, MK>, grid, rg.threads, smem, as_stream(stream),                   \
       (const T*)dy, w_packed, (T*)dx, g, (const T*)mask_src, mask_scale, mask_shift, splits, stats, P, rg.cv,   \
       rg.rows, rg.chunk)
   X3D_DISPATCH_DTYPE(dt, {
@@ -279,6 +281,7 @@ __global__ void dw_wgrad_direct_kernel(const T* __restrict__ x, const T* __restr
                                        DwGeom g, int C, const float* __restrict__ scale,
                                        const float* __restrict__ shift, int splits, int64_t P /*out positions*/,
                                        int cv, int rows, int64_t chunk) {
+  x3d::pdl_prologue();
   extern __shared__ float s_w[];  // [KH*KW][Cp]
   constexpr int VEC = Vec<T>::N;
   constexpr int NT = KH * KW;
@@ -365,7 +368,7 @@ extern "C" int x3d_dwconv_wgrad(const void* x, const void* dy, float* dw, int64_
     if (handled) return rc;
   }
 #define L_(KT_, KH_, KW_, XF, RL)                                                                               \
-  dw_wgrad_direct_kernel<T, KT_, KH_, KW_, XF, RL><<<grid, rg.threads, smem, as_stream(stream)>>>(              \
+  x3d::launch(dw_wgrad_direct_kernel<T, KT_, KH_, KW_, XF, RL>, grid, rg.threads, smem, as_stream(stream),               \
       (const T*)x, (const T*)dy, dw, g, (int)C, in_scale, in_shift, splits, P, rg.cv, rg.rows, rg.chunk)
   X3D_DISPATCH_DTYPE(dt, {
     RowGeom rg = make_row_geom<T>(N, P, Cp, 2 * kNumSMs);

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(Cfg<PW>::MAXT, Cfg<PW>::MINB)
 dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w, T* __restrict__ y,
                  const TileGeom g, const float* __restrict__ scale, const float* __restrict__ shift, int splits,
                  const T* __restrict__ aux, double* __restrict__ stats) {
+  x3d::pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using M = Map<MODE>;
   constexpr int WR = M::in_ext(PH), WC = M::in_ext(PW);         // per-thread input window
@@ -187,6 +188,7 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
   __syncthreads();
+  x3d::pdl_wait();                         // on-chip setup done; global memory is touched only from here on
   auto issue = [&](int t, int slot) {      // one thread: arm the barrier, fire one TMA box load
     mbar_expect_tx(&full_bar[slot], plane_bytes);
     tma_load_5d(sbuf + slot * g.stage_elems, &tmap, &full_bar[slot], cbase, wi0, hi0, t, n);
@@ -467,7 +469,7 @@ void launch_one(const TilePlan& p, const CUtensorMap& map, const Args& a, cudaSt
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  kfn<<<p.grid, p.threads, p.smem, stream>>>(map, a.w, (T*)a.y, p.g, a.scale, a.shift, a.splits, (const T*)a.aux,
+  x3d::launch(kfn, p.grid, p.threads, p.smem, stream, map, a.w, (T*)a.y, p.g, a.scale, a.shift, a.splits, (const T*)a.aux,
                                              a.stats);
 }
 
@@ -520,6 +522,7 @@ __global__ void __launch_bounds__(Cfg<PW>::MAXT, Cfg<PW>::MINB)
 dw3_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap dymap,
                        float* __restrict__ dw, const TileGeom g, const float* __restrict__ scale,
                        const float* __restrict__ shift, int splits, int C, int dy_stage_elems) {
+  x3d::pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using M = Map<MODE>;                                           // forward geometry (MODE = M_FWD1 / M_FWD2)
   constexpr int WR = M::in_ext(PH), WC = M::in_ext(PW);
@@ -556,6 +559,7 @@ dw3_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_co
   }
   for (int i = tid; i < 27 * CC; i += nthr) s_red[i] = 0.f;
   __syncthreads();
+  x3d::pdl_wait();
   // step s (s = -1 .. T-1) needs x[s] (if s >= 0) and dy[s+1] (if s+1 < T)
   auto issue = [&](int s, int slot) {
     const bool hx = s >= 0, hd = s + 1 < nT;
@@ -677,7 +681,7 @@ void launch_wgrad_one(const TilePlan& p, const CUtensorMap& xmap, const CUtensor
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  kfn<<<p.grid, p.threads, smem, stream>>>(xmap, dymap, dw, p.g, scale, shift, splits, C, dy_stage_elems);
+  x3d::launch(kfn, p.grid, p.threads, smem, stream, xmap, dymap, dw, p.g, scale, shift, splits, C, dy_stage_elems);
 }
 
 // x: [N][T_][H][W][Cp] (conv input), dy: [N][T_][Ho][Wo][Cp]

@@ -3,6 +3,7 @@
 // head pooling.  All activation tensors are [N][P][Cp] (NDHWC, Cp % 8 == 0), accessed with
 // 16-byte vectors; block = (channel vectors) x (position rows), grid = (chunks, N).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -16,6 +17,10 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static const bool on = getenv("X3D_NO_PDL") == nullptr;
+  return on;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace x3d
@@ -43,6 +48,7 @@ extern "C" int64_t x3d_launch_count(void) { return x3d::g_launches.load(); }
 template <typename T>
 __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int Cp,
                                       int64_t S /*T*H*W*/) {
+  x3d::pdl_prologue();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t s0 = (int64_t)blockIdx.x * 32;
@@ -62,6 +68,7 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ src, T* __restri
 template <typename T>
 __global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int Cp,
                                       int64_t S) {
+  x3d::pdl_prologue();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int64_t s0 = (int64_t)blockIdx.x * 32;
@@ -85,7 +92,7 @@ extern "C" int x3d_ncdhw_to_ndhwc(const float* src, void* dst, int64_t N, int64_
   int64_t S = T_ * H * W;
   if (N * S == 0) return 0;
   dim3 grid((unsigned)cdiv(S, 32), (unsigned)cdiv(Cp, 32), (unsigned)N), block(32, 8);
-  X3D_DISPATCH_DTYPE(dt, (ncdhw_to_ndhwc_kernel<T><<<grid, block, 0, as_stream(stream)>>>(src, (T*)dst, (int)C, (int)Cp, S)));
+  X3D_DISPATCH_DTYPE(dt, (x3d::launch(ncdhw_to_ndhwc_kernel<T>, grid, block, 0, as_stream(stream), src, (T*)dst, (int)C, (int)Cp, S)));
   X3D_LAUNCH_CHECK();
   return 0;
 }
@@ -95,7 +102,7 @@ extern "C" int x3d_ndhwc_to_ncdhw(const void* src, float* dst, int64_t N, int64_
   int64_t S = T_ * H * W;
   if (N * S == 0) return 0;
   dim3 grid((unsigned)cdiv(S, 32), (unsigned)cdiv(C, 32), (unsigned)N), block(32, 8);
-  X3D_DISPATCH_DTYPE(dt, (ndhwc_to_ncdhw_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)src, dst, (int)C, (int)Cp, S)));
+  X3D_DISPATCH_DTYPE(dt, (x3d::launch(ndhwc_to_ncdhw_kernel<T>, grid, block, 0, as_stream(stream), (const T*)src, dst, (int)C, (int)Cp, S)));
   X3D_LAUNCH_CHECK();
   return 0;
 }
@@ -104,6 +111,7 @@ extern "C" int x3d_ndhwc_to_ncdhw(const void* src, float* dst, int64_t N, int64_
 // parameter repack (one launch for the whole network)
 // =======================================================================================
 __global__ void pack_params_kernel(const x3d_pack_desc_t* __restrict__ descs) {
+  x3d::pdl_prologue();
   const x3d_pack_desc_t d = descs[blockIdx.y];
   const int64_t total = (int64_t)d.dst_rows * d.dst_cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -123,7 +131,7 @@ extern "C" int x3d_pack_params(const x3d_pack_desc_t* descs_dev, int n_desc, int
   int64_t bx = cdiv(max_dst_elems, 256);
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
-  pack_params_kernel<<<dim3((unsigned)bx, (unsigned)n_desc), 256, 0, as_stream(stream)>>>(descs_dev);
+  x3d::launch(pack_params_kernel, dim3((unsigned)bx, (unsigned)n_desc), 256, 0, as_stream(stream), descs_dev);
   X3D_LAUNCH_CHECK();
   return 0;
 }
@@ -159,6 +167,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int 
                                    int64_t* __restrict__ nbt, float momentum, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+  x3d::pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx == 0 && nbt) *nbt += 1;
   if (idx >= splits * Cp) return;
@@ -192,7 +201,7 @@ extern "C" int x3d_bn_finalize(const double* stats, int64_t N, int splits, int64
                                float* mean, float* rstd, x3d_stream_t stream) {
   X3D_CHECK_ARG(splits >= 1 && N % splits == 0, "batch must be divisible by num_splits (x3d.py:50)");
   int total = (int)(splits * Cp);
-  bn_finalize_kernel<<<(unsigned)cdiv(total, 128), 128, 0, as_stream(stream)>>>(
+  x3d::launch(bn_finalize_kernel, (unsigned)cdiv(total, 128), 128, 0, as_stream(stream), 
       stats, (int)N, splits, (double)P, (int)C, (int)Cp, gamma, beta, run_mean, run_var, nbt, momentum, eps, scale,
       shift, mean, rstd);
   X3D_LAUNCH_CHECK();
@@ -202,6 +211,7 @@ extern "C" int x3d_bn_finalize(const double* stats, int64_t N, int splits, int64
 __global__ void bn_eval_params_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ rm, const float* __restrict__ rv, int C, int Cp,
                                       float eps, float* scale, float* shift, float* mean, float* rstd) {
+  x3d::pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cp) return;
   float sc = 0.f, sh = 0.f, mu = 0.f, r = 0.f;
@@ -218,7 +228,7 @@ __global__ void bn_eval_params_kernel(const float* __restrict__ gamma, const flo
 extern "C" int x3d_bn_eval_params(const float* gamma, const float* beta, const float* run_mean,
                                   const float* run_var, int64_t C, int64_t Cp, float eps, float* scale,
                                   float* shift, float* mean, float* rstd, x3d_stream_t stream) {
-  bn_eval_params_kernel<<<(unsigned)cdiv(Cp, 128), 128, 0, as_stream(stream)>>>(gamma, beta, run_mean, run_var, (int)C,
+  x3d::launch(bn_eval_params_kernel, (unsigned)cdiv(Cp, 128), 128, 0, as_stream(stream), gamma, beta, run_mean, run_var, (int)C,
                                                                             (int)Cp, eps, scale, shift, mean, rstd);
   X3D_LAUNCH_CHECK();
   return 0;
@@ -232,6 +242,7 @@ __global__ void bn_act_fwd_kernel(const T* __restrict__ a, const float* __restri
                                   const float* __restrict__ shift, int splits, const T* __restrict__ res,
                                   const float* __restrict__ rscale, const float* __restrict__ rshift,
                                   T* __restrict__ out, int64_t P, int Cp, int cv, int rows, int64_t chunk) {
+  x3d::pdl_prologue();
   ROW_PROLOGUE();
   const int b = n % splits;
   float sc[VEC], sh[VEC], rs[VEC], rh[VEC];
@@ -266,7 +277,7 @@ extern "C" int x3d_bn_act_fwd(const void* a, const float* scale, const float* sh
   if (N * P == 0) return 0;
   const int mode = res ? (res_scale ? 2 : 1) : 0;
 #define LAUNCH_(M, R)                                                                                          \
-  bn_act_fwd_kernel<T, M, R><<<grid, g.threads, 0, as_stream(stream)>>>((const T*)a, scale, shift, splits,      \
+  x3d::launch(bn_act_fwd_kernel<T, M, R>, grid, g.threads, 0, as_stream(stream), (const T*)a, scale, shift, splits,      \
                                                                          (const T*)res, res_scale, res_shift,  \
                                                                          (T*)out, P, (int)Cp, g.cv, g.rows, g.chunk)
   X3D_DISPATCH_DTYPE(dt, {
@@ -291,6 +302,7 @@ template <typename T, bool MASK>
 __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ mask_out,
                                      const T* __restrict__ a, double* __restrict__ stats, int64_t P, int Cp, int cv,
                                      int rows, int64_t chunk) {
+  x3d::pdl_prologue();
   extern __shared__ float s_acc[];
   ROW_PROLOGUE();
   float a0[VEC], a1[VEC];
@@ -320,10 +332,10 @@ extern "C" int x3d_bn_bwd_reduce(const void* dout, const void* mask_out, const v
     dim3 grid(g.chunks, (unsigned)N);
     size_t smem = (size_t)g.rows * Cp * 2 * sizeof(float);
     if (mask_out)
-      bn_bwd_reduce_kernel<T, true><<<grid, g.threads, smem, as_stream(stream)>>>(
+      x3d::launch(bn_bwd_reduce_kernel<T, true>, grid, g.threads, smem, as_stream(stream), 
           (const T*)dout, (const T*)mask_out, (const T*)a, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
     else
-      bn_bwd_reduce_kernel<T, false><<<grid, g.threads, smem, as_stream(stream)>>>(
+      x3d::launch(bn_bwd_reduce_kernel<T, false>, grid, g.threads, smem, as_stream(stream), 
           (const T*)dout, nullptr, (const T*)a, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
   });
   X3D_LAUNCH_CHECK();
@@ -335,6 +347,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int N, 
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ rstd, int train, float* __restrict__ coef,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  x3d::pdl_prologue();
   // one thread per (split, channel)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int sC = splits * Cp;
@@ -365,7 +378,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int N, 
 extern "C" int x3d_bn_bwd_finalize(const double* stats, int64_t N, int splits, int64_t P, int64_t C, int64_t Cp,
                                    const float* gamma, const float* mean, const float* rstd, int train,
                                    float* coef, float* dgamma, float* dbeta, x3d_stream_t stream) {
-  bn_bwd_finalize_kernel<<<(unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream)>>>(stats, (int)N, splits, (double)P, (int)C,
+  x3d::launch(bn_bwd_finalize_kernel, (unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream), stats, (int)N, splits, (double)P, (int)C,
                                                                             (int)Cp, gamma, mean, rstd, train, coef,
                                                                             dgamma, dbeta);
   X3D_LAUNCH_CHECK();
@@ -376,6 +389,7 @@ template <typename T, bool MASK>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ mask_out,
                                     const T* __restrict__ a, const float* __restrict__ coef, int splits,
                                     T* __restrict__ da, int64_t P, int Cp, int cv, int rows, int64_t chunk) {
+  x3d::pdl_prologue();
   ROW_PROLOGUE();
   const int b = n % splits;
   const int sC = splits * Cp;
@@ -409,10 +423,10 @@ extern "C" int x3d_bn_bwd_apply(const void* dout, const void* mask_out, const vo
     RowGeom g = make_row_geom<T>(N, P, Cp, 8 * kNumSMs);
     dim3 grid(g.chunks, (unsigned)N);
     if (mask_out)
-      bn_bwd_apply_kernel<T, true><<<grid, g.threads, 0, as_stream(stream)>>>(
+      x3d::launch(bn_bwd_apply_kernel<T, true>, grid, g.threads, 0, as_stream(stream), 
           (const T*)dout, (const T*)mask_out, (const T*)a, coef, splits, (T*)da, P, (int)Cp, g.cv, g.rows, g.chunk);
     else
-      bn_bwd_apply_kernel<T, false><<<grid, g.threads, 0, as_stream(stream)>>>(
+      x3d::launch(bn_bwd_apply_kernel<T, false>, grid, g.threads, 0, as_stream(stream), 
           (const T*)dout, nullptr, (const T*)a, coef, splits, (T*)da, P, (int)Cp, g.cv, g.rows, g.chunk);
   });
   X3D_LAUNCH_CHECK();
@@ -422,6 +436,7 @@ extern "C" int x3d_bn_bwd_apply(const void* dout, const void* mask_out, const vo
 template <typename T>
 __global__ void relu_bwd_add_kernel(const T* __restrict__ dout, const T* __restrict__ out, T* __restrict__ dx,
                                     int64_t nvec) {
+  x3d::pdl_prologue();
   constexpr int VEC = Vec<T>::N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float d[VEC], o[VEC], x[VEC];
@@ -441,7 +456,7 @@ extern "C" int x3d_relu_bwd_add(const void* dout, const void* out, void* dx, int
     int64_t nvec = numel / Vec<T>::N;
     int64_t blocks = cdiv(nvec, 256);
     if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
-    relu_bwd_add_kernel<T><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const T*)dout, (const T*)out, (T*)dx, nvec);
+    x3d::launch(relu_bwd_add_kernel<T>, (unsigned)blocks, 256, 0, as_stream(stream), (const T*)dout, (const T*)out, (T*)dx, nvec);
   });
   X3D_LAUNCH_CHECK();
   return 0;
@@ -455,6 +470,7 @@ __global__ void se_fwd_kernel(const double* __restrict__ stats, const float* __r
                               const float* __restrict__ W1, const float* __restrict__ b1,
                               const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ pooled,
                               float* __restrict__ hidden, float* __restrict__ gate) {
+  x3d::pdl_prologue();
   extern __shared__ float sm[];
   float* s_p = sm;        // [C]
   float* s_h = sm + C;    // [sw]
@@ -495,7 +511,7 @@ extern "C" int x3d_se_fwd(const double* stats, const float* scale, const float* 
                           x3d_stream_t stream) {
   if (N == 0) return 0;
   size_t smem = (C + sw) * sizeof(float);
-  se_fwd_kernel<<<(unsigned)N, 256, smem, as_stream(stream)>>>(stats, scale, shift, splits, 1.0 / (double)P, (int)C,
+  x3d::launch(se_fwd_kernel, (unsigned)N, 256, smem, as_stream(stream), stats, scale, shift, splits, 1.0 / (double)P, (int)C,
                                                               (int)Cp, sw, W1, b1, W2, b2, pooled, hidden, gate);
   X3D_LAUNCH_CHECK();
   return 0;
@@ -508,6 +524,7 @@ template <typename T, bool GATE>
 __global__ void swish_gate_fwd_kernel(const T* __restrict__ a2, const float* __restrict__ scale,
                                       const float* __restrict__ shift, int splits, const float* __restrict__ gate,
                                       T* __restrict__ v, int64_t P, int Cp, int cv, int rows, int64_t chunk) {
+  x3d::pdl_prologue();
   ROW_PROLOGUE();
   const int b = n % splits;
   float sc[VEC], sh[VEC];
@@ -538,10 +555,10 @@ extern "C" int x3d_swish_gate_fwd(const void* a2, const float* scale, const floa
     RowGeom g = make_row_geom<T>(N, P, Cp, 8 * kNumSMs);
     dim3 grid(g.chunks, (unsigned)N);
     if (gate)
-      swish_gate_fwd_kernel<T, true><<<grid, g.threads, 0, as_stream(stream)>>>((const T*)a2, scale, shift, splits, gate,
+      x3d::launch(swish_gate_fwd_kernel<T, true>, grid, g.threads, 0, as_stream(stream), (const T*)a2, scale, shift, splits, gate,
                                                                                (T*)v, P, (int)Cp, g.cv, g.rows, g.chunk);
     else
-      swish_gate_fwd_kernel<T, false><<<grid, g.threads, 0, as_stream(stream)>>>((const T*)a2, scale, shift, splits,
+      x3d::launch(swish_gate_fwd_kernel<T, false>, grid, g.threads, 0, as_stream(stream), (const T*)a2, scale, shift, splits,
                                                                                 nullptr, (T*)v, P, (int)Cp, g.cv, g.rows,
                                                                                 g.chunk);
   });
@@ -560,6 +577,7 @@ __global__ void swish_gate_bwd_reduce_kernel(const T* __restrict__ dv, const T* 
                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                              int splits, const float* __restrict__ gate, double* __restrict__ stats,
                                              int64_t P, int Cp, int cv, int rows, int64_t chunk) {
+  x3d::pdl_prologue();
   extern __shared__ float s_acc[];
   ROW_PROLOGUE();
   const int b = n % splits;
@@ -595,10 +613,10 @@ extern "C" int x3d_swish_gate_bwd_reduce(const void* dv, const void* a2, const f
     dim3 grid(g.chunks, (unsigned)N);
     size_t smem = (size_t)g.rows * Cp * 2 * sizeof(float);
     if (gate)
-      swish_gate_bwd_reduce_kernel<T, true><<<grid, g.threads, smem, as_stream(stream)>>>(
+      x3d::launch(swish_gate_bwd_reduce_kernel<T, true>, grid, g.threads, smem, as_stream(stream), 
           (const T*)dv, (const T*)a2, scale, shift, splits, gate, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
     else
-      swish_gate_bwd_reduce_kernel<T, false><<<grid, g.threads, smem, as_stream(stream)>>>(
+      x3d::launch(swish_gate_bwd_reduce_kernel<T, false>, grid, g.threads, smem, as_stream(stream), 
           (const T*)dv, (const T*)a2, scale, shift, splits, nullptr, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
   });
   X3D_LAUNCH_CHECK();
@@ -614,6 +632,7 @@ __global__ void se_bwd_sample_kernel(const double* __restrict__ fwd_stats, const
                                      const float* __restrict__ hidden, const float* __restrict__ gate,
                                      float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
                                      float* __restrict__ db2, float* __restrict__ work) {
+  x3d::pdl_prologue();
   extern __shared__ float sm[];
   float* s_dz2 = sm;           // [C]
   float* s_dz1 = sm + C;       // [sw]
@@ -667,6 +686,7 @@ __global__ void se_bn_bwd_coef_kernel(const double* __restrict__ fwd_stats, cons
                                       const float* __restrict__ gate /*nullable*/, const float* __restrict__ work,
                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
                                       float* __restrict__ coef) {
+  x3d::pdl_prologue();
   // one thread per (split, channel)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= splits * Cp) return;
@@ -723,12 +743,12 @@ extern "C" int x3d_se_bn_bwd(const double* fwd_stats, const double* bwd_stats, i
   if (N == 0) return 0;
   if (gate) {
     size_t smem = (C + 2 * sw) * sizeof(float);
-    se_bwd_sample_kernel<<<(unsigned)N, 256, smem, as_stream(stream)>>>(fwd_stats, bwd_stats, splits, (double)P, (int)C,
+    x3d::launch(se_bwd_sample_kernel, (unsigned)N, 256, smem, as_stream(stream), fwd_stats, bwd_stats, splits, (double)P, (int)C,
                                                                        (int)Cp, sw, scale, shift, W1, W2, pooled, hidden,
                                                                        gate, dW1, db1, dW2, db2, work);
     X3D_LAUNCH_CHECK();
   }
-  se_bn_bwd_coef_kernel<<<(unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream)>>>(fwd_stats, bwd_stats, (int)N, splits,
+  x3d::launch(se_bn_bwd_coef_kernel, (unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream), fwd_stats, bwd_stats, (int)N, splits,
                                                                            (double)P, (int)C, (int)Cp, gamma, mean, rstd,
                                                                            train, gate, work, dgamma, dbeta, coef);
   X3D_LAUNCH_CHECK();
@@ -740,6 +760,7 @@ __global__ void swish_gate_bwd_apply_kernel(const T* __restrict__ dv, const T* _
                                             const float* __restrict__ scale, const float* __restrict__ shift,
                                             int splits, const float* __restrict__ gate, const float* __restrict__ coef,
                                             T* __restrict__ da2, int64_t P, int Cp, int cv, int rows, int64_t chunk) {
+  x3d::pdl_prologue();
   ROW_PROLOGUE();
   const int b = n % splits;
   float sc[VEC], sh[VEC], E1[VEC], E2[VEC], E3[VEC];
@@ -773,10 +794,10 @@ extern "C" int x3d_swish_gate_bwd_apply(const void* dv, const void* a2, const fl
     RowGeom g = make_row_geom<T>(N, P, Cp, 8 * kNumSMs);
     dim3 grid(g.chunks, (unsigned)N);
     if (gate)
-      swish_gate_bwd_apply_kernel<T, true><<<grid, g.threads, 0, as_stream(stream)>>>(
+      x3d::launch(swish_gate_bwd_apply_kernel<T, true>, grid, g.threads, 0, as_stream(stream), 
           (const T*)dv, (const T*)a2, scale, shift, splits, gate, coef, (T*)da2, P, (int)Cp, g.cv, g.rows, g.chunk);
     else
-      swish_gate_bwd_apply_kernel<T, false><<<grid, g.threads, 0, as_stream(stream)>>>(
+      x3d::launch(swish_gate_bwd_apply_kernel<T, false>, grid, g.threads, 0, as_stream(stream), 
           (const T*)dv, (const T*)a2, scale, shift, splits, nullptr, coef, (T*)da2, P, (int)Cp, g.cv, g.rows, g.chunk);
   });
   X3D_LAUNCH_CHECK();
@@ -792,6 +813,7 @@ __global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ a, const float* __
                                         const float* __restrict__ shift, int splits, float* __restrict__ pooled,
                                         int rows_per_sample, int64_t P /*positions per row*/, int C, int Cp, int cv,
                                         int rows, int64_t chunk) {
+  x3d::pdl_prologue();
   extern __shared__ float s_acc[];
   ROW_PROLOGUE();   // here "n" is the pooled row r
   const int b = (n / rows_per_sample) % splits;
@@ -830,7 +852,7 @@ extern "C" int x3d_bn_relu_pool_fwd(const void* a5, const float* scale, const fl
   X3D_DISPATCH_DTYPE(dt, {
     RowGeom g = make_row_geom<T>(R, Pp, Cp);
     dim3 grid(g.chunks, (unsigned)R);
-    bn_relu_pool_fwd_kernel<T><<<grid, g.threads, Cp * sizeof(float), as_stream(stream)>>>(
+    x3d::launch(bn_relu_pool_fwd_kernel<T>, grid, g.threads, Cp * sizeof(float), as_stream(stream), 
         (const T*)a5, scale, shift, splits, pooled, pool_t ? 1 : (int)T_, Pp, (int)C, (int)Cp, g.cv, g.rows, g.chunk);
   });
   X3D_LAUNCH_CHECK();
@@ -843,6 +865,7 @@ __global__ void bn_relu_pool_bwd_kernel(const T* __restrict__ a, const float* __
                                         const float* __restrict__ dpooled, double* __restrict__ stats,
                                         const float* __restrict__ coef, T* __restrict__ da, int rows_per_sample,
                                         int64_t P, int C, int Cp, int cv, int rows, int64_t chunk) {
+  x3d::pdl_prologue();
   extern __shared__ float s_acc[];
   ROW_PROLOGUE();   // n = pooled row r
   const int ns = n / rows_per_sample;   // sample index
@@ -890,7 +913,7 @@ extern "C" int x3d_bn_relu_pool_bwd_reduce(const void* a5, const float* scale, c
   X3D_DISPATCH_DTYPE(dt, {
     RowGeom g = make_row_geom<T>(R, Pp, Cp);
     dim3 grid(g.chunks, (unsigned)R);
-    bn_relu_pool_bwd_kernel<T, false><<<grid, g.threads, (size_t)g.rows * Cp * 2 * sizeof(float), as_stream(stream)>>>(
+    x3d::launch(bn_relu_pool_bwd_kernel<T, false>, grid, g.threads, (size_t)g.rows * Cp * 2 * sizeof(float), as_stream(stream), 
         (const T*)a5, scale, shift, splits, dpooled, stats, nullptr, nullptr, pool_t ? 1 : (int)T_, Pp, (int)C, (int)Cp,
         g.cv, g.rows, g.chunk);
   });
@@ -908,7 +931,7 @@ extern "C" int x3d_bn_relu_pool_bwd_apply(const void* a5, const float* scale, co
   X3D_DISPATCH_DTYPE(dt, {
     RowGeom g = make_row_geom<T>(R, Pp, Cp, 8 * kNumSMs);
     dim3 grid(g.chunks, (unsigned)R);
-    bn_relu_pool_bwd_kernel<T, true><<<grid, g.threads, Cp * 2 * sizeof(float), as_stream(stream)>>>(
+    x3d::launch(bn_relu_pool_bwd_kernel<T, true>, grid, g.threads, Cp * 2 * sizeof(float), as_stream(stream), 
         (const T*)a5, scale, shift, splits, dpooled, nullptr, coef, (T*)da5, pool_t ? 1 : (int)T_, Pp, (int)C, (int)Cp,
         g.cv, g.rows, g.chunk);
   });
@@ -923,6 +946,7 @@ __global__ void small_gemm_kernel(const float* __restrict__ A, int64_t sai, int6
                                   int64_t sbk, int64_t sbj, float* __restrict__ C, int64_t ldc, int M, int Nn, int K,
                                   const float* __restrict__ bias, int relu, const float* __restrict__ mul,
                                   int accumulate) {
+  x3d::pdl_prologue();
   __shared__ float As[32][33];  // [i][k]
   __shared__ float Bs[32][33];  // [k][j]
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
@@ -971,6 +995,7 @@ __global__ void skinny_gemm_kcontig_kernel(const float* __restrict__ A, int64_t 
                                            const float* __restrict__ B, int64_t sbj, float* __restrict__ C, int64_t ldc,
                                            int M, int Nn, int K, const float* __restrict__ bias, int relu,
                                            const float* __restrict__ mul, int accumulate) {
+  x3d::pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (warp >= Nn) return;
   const int j = warp;
@@ -1007,6 +1032,7 @@ template <int MR>
 __global__ void skinny_gemm_jcontig_kernel(const float* __restrict__ A, int64_t sai, int64_t sak,
                                            const float* __restrict__ B, int64_t sbk, float* __restrict__ C, int64_t ldc,
                                            int M, int Nn, int K, int kchunk) {
+  x3d::pdl_prologue();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Nn) return;
   const int k0 = blockIdx.y * kchunk;
@@ -1031,7 +1057,7 @@ extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const fl
   if (M == 0 || Nn == 0) return 0;
   if (M <= 32 && sbk == 1) {
     const int64_t threads = Nn * 32;
-#define SK_(MR) skinny_gemm_kcontig_kernel<MR><<<(unsigned)cdiv(threads, 256), 256, 0, as_stream(stream)>>>( \
+#define SK_(MR) x3d::launch(skinny_gemm_kcontig_kernel<MR>, (unsigned)cdiv(threads, 256), 256, 0, as_stream(stream),  \
       A, sai, sak, B, sbj, C, ldc, (int)M, (int)Nn, (int)K, bias, relu, mul, accumulate)
     if (M <= 8) SK_(8); else if (M <= 16) SK_(16); else SK_(32);
 #undef SK_
@@ -1042,13 +1068,13 @@ extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const fl
     }
     const int kchunk = 64;
     dim3 grid((unsigned)cdiv(Nn, 64), (unsigned)cdiv(K, kchunk));
-#define SJ_(MR) skinny_gemm_jcontig_kernel<MR><<<grid, 64, 0, as_stream(stream)>>>( \
+#define SJ_(MR) x3d::launch(skinny_gemm_jcontig_kernel<MR>, grid, 64, 0, as_stream(stream),  \
       A, sai, sak, B, sbk, C, ldc, (int)M, (int)Nn, (int)K, kchunk)
     if (M <= 8) SJ_(8); else if (M <= 16) SJ_(16); else SJ_(32);
 #undef SJ_
   } else {
     dim3 grid((unsigned)cdiv(Nn, 32), (unsigned)cdiv(M, 32)), block(32, 8);
-    small_gemm_kernel<<<grid, block, 0, as_stream(stream)>>>(A, sai, sak, B, sbk, sbj, C, ldc, (int)M, (int)Nn, (int)K,
+    x3d::launch(small_gemm_kernel, grid, block, 0, as_stream(stream), A, sai, sak, B, sbk, sbj, C, ldc, (int)M, (int)Nn, (int)K,
                                                             bias, relu, mul, accumulate);
   }
   X3D_LAUNCH_CHECK();
@@ -1056,6 +1082,7 @@ extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const fl
 }
 
 __global__ void colsum_kernel(const float* __restrict__ src, int M, int Nn, float* __restrict__ dst) {
+  x3d::pdl_prologue();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Nn) return;
   float acc = 0.f;
@@ -1064,13 +1091,14 @@ __global__ void colsum_kernel(const float* __restrict__ src, int M, int Nn, floa
 }
 extern "C" int x3d_colsum(const float* src, int64_t M, int64_t Nn, float* dst, x3d_stream_t stream) {
   if (Nn == 0) return 0;
-  colsum_kernel<<<(unsigned)cdiv(Nn, 128), 128, 0, as_stream(stream)>>>(src, (int)M, (int)Nn, dst);
+  x3d::launch(colsum_kernel, (unsigned)cdiv(Nn, 128), 128, 0, as_stream(stream), src, (int)M, (int)Nn, dst);
   X3D_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void relu_mask_mul_kernel(const float* __restrict__ src, const float* __restrict__ ref,
                                      const float* __restrict__ mul, float* __restrict__ dst, int64_t n) {
+  x3d::pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = ref[i] > 0.f ? src[i] : 0.f;
     if (mul) v *= mul[i];
@@ -1082,7 +1110,7 @@ extern "C" int x3d_relu_mask_mul(const float* src, const float* ref, const float
   if (numel == 0) return 0;
   int64_t blocks = cdiv(numel, 256);
   if (blocks > 1024) blocks = 1024;
-  relu_mask_mul_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, ref, mul, dst, numel);
+  x3d::launch(relu_mask_mul_kernel, (unsigned)blocks, 256, 0, as_stream(stream), src, ref, mul, dst, numel);
   X3D_LAUNCH_CHECK();
   return 0;
 }
@@ -1092,6 +1120,7 @@ extern "C" int x3d_relu_mask_mul(const float* src, const float* ref, const float
 // =======================================================================================
 __global__ void sgd_kernel(const x3d_sgd_desc_t* __restrict__ descs, float lr, float momentum, float wd,
                            float grad_scale, int first_step, const float* __restrict__ hyper) {
+  x3d::pdl_prologue();
   if (hyper) { lr = hyper[0]; momentum = hyper[1]; wd = hyper[2]; grad_scale = hyper[3]; }
   const x3d_sgd_desc_t d = descs[blockIdx.y];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.numel; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1112,7 +1141,7 @@ extern "C" int x3d_sgd_step(const x3d_sgd_desc_t* descs_dev, int n_desc, int64_t
   int64_t bx = cdiv(max_numel, 256 * 4);
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
-  sgd_kernel<<<dim3((unsigned)bx, (unsigned)n_desc), 256, 0, as_stream(stream)>>>(descs_dev, lr, momentum, weight_decay,
+  x3d::launch(sgd_kernel, dim3((unsigned)bx, (unsigned)n_desc), 256, 0, as_stream(stream), descs_dev, lr, momentum, weight_decay,
                                                                               grad_scale, first_step, nullptr);
   X3D_LAUNCH_CHECK();
   return 0;
@@ -1124,7 +1153,7 @@ extern "C" int x3d_sgd_step_dev(const x3d_sgd_desc_t* descs_dev, int n_desc, int
   int64_t bx = cdiv(max_numel, 256 * 4);
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
-  sgd_kernel<<<dim3((unsigned)bx, (unsigned)n_desc), 256, 0, as_stream(stream)>>>(descs_dev, 0.f, 0.f, 0.f, 1.f, first_step,
+  x3d::launch(sgd_kernel, dim3((unsigned)bx, (unsigned)n_desc), 256, 0, as_stream(stream), descs_dev, 0.f, 0.f, 0.f, 1.f, first_step,
                                                                               hyper_dev);
   X3D_LAUNCH_CHECK();
   return 0;

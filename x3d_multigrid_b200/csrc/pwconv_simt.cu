@@ -35,6 +35,7 @@ template <typename T, bool MAP_A, bool MAP_C, bool STATS, bool ACCUM>
 __global__ void __launch_bounds__(256) pw_gemm_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B,
                                                        int ldb, T* __restrict__ C, int ldc, int64_t M, int K, int Nn,
                                                        RowMap map, int64_t P_out, double* __restrict__ stats) {
+  x3d::pdl_prologue();
   constexpr int VEC = Vec<T>::N;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -174,7 +175,7 @@ extern "C" int x3d_pwconv_fwd(const void* x, const void* w, void* y, int64_t N, 
   }
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(Np, BN));
 #define L_(MA, ST)                                                                                           \
-  pw_gemm_kernel<T, MA, false, ST, false><<<grid, 256, 0, as_stream(stream)>>>(                              \
+  x3d::launch(pw_gemm_kernel<T, MA, false, ST, false>, grid, 256, 0, as_stream(stream),                               \
       (const T*)x, (int)Kp, (const T*)w, (int)Kp, (T*)y, (int)Np, M, (int)Kp, (int)Np, map, P_out, stats)
   X3D_DISPATCH_DTYPE(dt, {
     if (stride != 1 && stats) L_(true, true);
@@ -204,7 +205,7 @@ extern "C" int x3d_pwconv_dgrad(const void* dy, const void* wT, void* dx, int64_
   // GEMM roles: A = dy [M][Np], B = wT [Kp][Np] (row k holds the Np coefficients), C = dx [.][Kp]
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(Kp, BN));
 #define L_(MC, AC)                                                                                           \
-  pw_gemm_kernel<T, false, MC, false, AC><<<grid, 256, 0, as_stream(stream)>>>(                              \
+  x3d::launch(pw_gemm_kernel<T, false, MC, false, AC>, grid, 256, 0, as_stream(stream),                               \
       (const T*)dy, (int)Np, (const T*)wT, (int)Np, (T*)dx, (int)Kp, M, (int)Np, (int)Kp, map, P_out, nullptr)
   X3D_DISPATCH_DTYPE(dt, {
     if (stride != 1 && accumulate) L_(true, true);
@@ -225,6 +226,7 @@ template <typename T, bool MAP_X>
 __global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ X, int ldx, const T* __restrict__ DY,
                                                         int ldy, float* __restrict__ dW, int64_t M, int K, int Kp,
                                                         int Nn, int Np, RowMap map, int64_t m_per_block) {
+  x3d::pdl_prologue();
   constexpr int VEC = Vec<T>::N;
   __shared__ __align__(16) float Ds[WM][64 + 4];
   __shared__ __align__(16) float Xs[WM][64 + 4];
@@ -310,10 +312,10 @@ extern "C" int x3d_pwconv_wgrad(const void* x, const void* dy, float* dw, int64_
   dim3 grid(nt, kt, (unsigned)splits);
   X3D_DISPATCH_DTYPE(dt, {
     if (stride != 1)
-      pw_wgrad_kernel<T, true><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (int)Kp, (const T*)dy, (int)Np, dw, M,
+      x3d::launch(pw_wgrad_kernel<T, true>, grid, 256, 0, as_stream(stream), (const T*)x, (int)Kp, (const T*)dy, (int)Np, dw, M,
                                                                    (int)K, (int)Kp, (int)Nn, (int)Np, map, mpb);
     else
-      pw_wgrad_kernel<T, false><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (int)Kp, (const T*)dy, (int)Np, dw, M,
+      x3d::launch(pw_wgrad_kernel<T, false>, grid, 256, 0, as_stream(stream), (const T*)x, (int)Kp, (const T*)dy, (int)Np, dw, M,
                                                                     (int)K, (int)Kp, (int)Nn, (int)Np, map, mpb);
   });
   X3D_LAUNCH_CHECK();

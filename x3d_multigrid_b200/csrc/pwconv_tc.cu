@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(NTHREADS)
 pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
              const __nv_bfloat16* __restrict__ A, __nv_bfloat16* __restrict__ C, const TcParams p,
              double* __restrict__ stats) {
+  x3d::pdl_trigger();
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms)
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -211,6 +212,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  x3d::pdl_wait();      // everything above was on-chip setup; global memory is touched only from here on
   // contiguous range of 128-row tiles of this CTA (keeps consecutive tiles in the same sample: statistics
   // are flushed once per sample, not once per tile)
   const int tpc = (p.tiles_m + gridDim.x - 1) / gridDim.x;
@@ -518,6 +520,7 @@ __global__ void __launch_bounds__(NTHREADS)
 pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
                    const __nv_bfloat16* __restrict__ DY, const __nv_bfloat16* __restrict__ X, float* __restrict__ dW,
                    const WgParams p) {
+  x3d::pdl_trigger();
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base = smem_dyn + (base_u32 - smem_u32(smem_dyn));
@@ -566,6 +569,7 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  x3d::pdl_wait();      // everything above was on-chip setup; global memory is touched only from here on
 
   if ((cpa_a || cpa_b) && warp != 1) {
     // narrow operand(s) (< 64 columns, i.e. < 128-byte rows): coalesced cp.async of the contiguous 64-row span
@@ -763,7 +767,7 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
   dim3 grid((unsigned)msplit, (unsigned)ntiles, (unsigned)kz);
   static const bool no_cpa = getenv("X3D_TC_NOCPA") != nullptr;
   p.cpa = no_cpa ? 0 : 1;
-  pw_wgrad_tc_kernel<<<grid, NTHREADS, smem, stream>>>(mapDY, mapX, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, p);
+  x3d::launch(pw_wgrad_tc_kernel, grid, NTHREADS, smem, stream, mapDY, mapX, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, p);
   *handled = true;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -828,10 +832,10 @@ int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, 
   static bool attr_done[2] = {false, false};
   if (stats) {
     if (!attr_done[1]) { cudaFuncSetAttribute(pw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done[1] = true; }
-    pw_tc_kernel<true><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, p, stats);
+    x3d::launch(pw_tc_kernel<true>, grid, NTHREADS, smem, stream, mapA, mapB, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, p, stats);
   } else {
     if (!attr_done[0]) { cudaFuncSetAttribute(pw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done[0] = true; }
-    pw_tc_kernel<false><<<grid, NTHREADS, smem, stream>>>(mapA, mapB, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, p, nullptr);
+    x3d::launch(pw_tc_kernel<false>, grid, NTHREADS, smem, stream, mapA, mapB, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, p, nullptr);
   }
   *handled = true;
   cudaError_t e = cudaGetLastError();

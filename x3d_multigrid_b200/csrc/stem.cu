@@ -11,6 +11,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         T* __restrict__ y, int Ci, int T_, int H, int W, int Ho,
                                                         int Wo, int Co, int Cop, int64_t total) {
+  x3d::pdl_prologue();
   extern __shared__ float s_w[];  // [taps][Cop]
   const int taps = Ci * 9;
   for (int i = threadIdx.x; i < taps * Cop; i += blockDim.x) {
@@ -80,7 +81,7 @@ extern "C" int x3d_stem_conv_s_fwd(const float* x, const float* w, void* y, int6
   const int64_t total = N * T_ * Ho * Wo;
   if (total == 0) return 0;
   size_t smem = (size_t)Ci * 9 * Cop * sizeof(float);
-  X3D_DISPATCH_DTYPE(dt, (stem_fwd_kernel<T><<<(unsigned)cdiv(total, 128), 128, smem, as_stream(stream)>>>(
+  X3D_DISPATCH_DTYPE(dt, (x3d::launch(stem_fwd_kernel<T>, (unsigned)cdiv(total, 128), 128, smem, as_stream(stream), 
                              x, w, (T*)y, (int)Ci, (int)T_, (int)H, (int)W, Ho, Wo, (int)Co, (int)Cop, total)));
   X3D_LAUNCH_CHECK();
   return 0;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
                                                           float* __restrict__ dw, int Ci, int T_, int H, int W,
                                                           int Ho, int Wo, int Co, int Cop, int64_t total,
                                                           int64_t pos_per_block) {
+  x3d::pdl_prologue();
   extern __shared__ float sm[];
   float* Xs = sm;                   // [SW_POS][32]
   float* Ds = sm + SW_POS * 32;     // [SW_POS][Cop]
@@ -213,7 +215,7 @@ extern "C" int x3d_stem_conv_s_wgrad(const float* x, const void* dy, float* dw, 
   int64_t ppb = cdiv(cdiv(total, blocks), SW_POS) * SW_POS;
   blocks = cdiv(total, ppb);
   size_t smem = (size_t)(SW_POS * 32 + SW_POS * Cop) * sizeof(float) + SW_POS * (sizeof(long long) + sizeof(int));
-  X3D_DISPATCH_DTYPE(dt, (stem_wgrad_kernel<T><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(
+  X3D_DISPATCH_DTYPE(dt, (x3d::launch(stem_wgrad_kernel<T>, (unsigned)blocks, 256, smem, as_stream(stream), 
                              x, (const T*)dy, dw, (int)Ci, (int)T_, (int)H, (int)W, Ho, Wo, (int)Co, (int)Cop, total, ppb)));
   X3D_LAUNCH_CHECK();
   return 0;
