@@ -10,7 +10,7 @@ using namespace x3d;
 
 namespace x3d {
 int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, int64_t Np, int64_t P_out,
-                  const int* gather, double* stats, cudaStream_t stream, bool* handled);
+                  const int* gather, const int* scatter, double* stats, cudaStream_t stream, bool* handled);
 int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t K, int64_t Kp, int64_t Nn,
                     int64_t Np, cudaStream_t stream, bool* handled);
 }
@@ -170,7 +170,7 @@ extern "C" int x3d_pwconv_fwd(const void* x, const void* w, void* y, int64_t N, 
   if (dt == X3D_BF16) {
     bool handled = false;
     const int gather[5] = {stride, (int)H, (int)W, map.Ho, map.Wo};
-    int rc = pwconv_fwd_tc(x, w, y, M, Kp, Np, P_out, stride > 1 ? gather : nullptr, stats, as_stream(stream), &handled);
+    int rc = pwconv_fwd_tc(x, w, y, M, Kp, Np, P_out, stride > 1 ? gather : nullptr, nullptr, stats, as_stream(stream), &handled);
     if (handled) return rc;
   }
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(Np, BN));
@@ -197,9 +197,12 @@ extern "C" int x3d_pwconv_dgrad(const void* dy, const void* wT, void* dx, int64_
   const int64_t P_out = T_ * map.Ho * map.Wo;
   const int64_t M = N * P_out;
   if (M == 0) return 0;
-  if (dt == X3D_BF16 && stride == 1 && !accumulate) {
+  if (dt == X3D_BF16 && (stride > 1 || !accumulate)) {
     bool handled = false;
-    int rc = pwconv_fwd_tc(dy, wT, dx, M, Np, Kp, P_out, nullptr, nullptr, as_stream(stream), &handled);
+    // strided conv: the dense GEMM rows (nt,ho,wo) land on rows (nt, s*ho, s*wo) of dx (untouched rows keep their value)
+    const int scatter[6] = {stride, (int)H, (int)W, map.Ho, map.Wo, accumulate};
+    int rc = pwconv_fwd_tc(dy, wT, dx, M, Np, Kp, P_out, nullptr, stride > 1 ? scatter : nullptr, nullptr,
+                           as_stream(stream), &handled);
     if (handled) return rc;
   }
   // GEMM roles: A = dy [M][Np], B = wT [Kp][Np] (row k holds the Np coefficients), C = dx [.][Kp]

@@ -105,6 +105,9 @@ struct TcParams {
   int cpitch;        // staging row pitch in elements (BN + 8: conflict-free 16-byte st.shared)
   int cpa;           // 1: A tile copied by cp.async (narrow rows), 0: by TMA
   int gs, gH, gW, gHo, gWo;   // row gather of a strided 1x1x1 conv: output row (nt,ho,wo) reads input row (nt, gs*ho, gs*wo)
+  int ss;            // row SCATTER (dgrad of a strided conv): GEMM row (nt,ho,wo) is written to row (nt, ss*ho, ss*wo)
+                     // of C (same gH,gW,gHo,gWo fields); ss = 0/1: dense
+  int accum;         // C += instead of C = (scatter mode: dx already holds the main-branch gradient)
   int dbg;           // profiling experiments (X3D_TC_DBG): 1 = skip copy-out, 2 = skip statistics, 4 = skip staging
   long long P_out;
 };
@@ -180,7 +183,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
   float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);      // [BN][2]
   float* s_part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_stat + 2 * BN) + 15) & ~(uintptr_t)15);
-  int* s_rowoff = reinterpret_cast<int*>(s_part + 1024);        // [128] gathered input rows of the current tile                              // [row groups][ncols][2] partial sums (<= 4 KB)
+  int* s_rowoff = reinterpret_cast<int*>(s_part + 1024);        // [128] gathered input rows of the current tile
+  int* s_rowout = s_rowoff + BM;                                 // [128] scattered output rows of the current tile                              // [row groups][ncols][2] partial sums (<= 4 KB)
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n0 = blockIdx.y * BN;
@@ -382,6 +386,13 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       const int m0 = tm * BM;
       // staging buffer is free (previous tile fully copied out / summed)
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (p.ss > 1) {                                       // scatter mode: output row of tile row `et`
+        const int m = m0 + et;
+        const int hw = p.gHo * p.gWo;
+        const int nt = m / hw, rem = m - nt * hw;
+        const int ho = rem / p.gWo, wo = rem - ho * p.gWo;
+        s_rowout[et] = (nt * p.gH + ho * p.ss) * p.gW + wo * p.ss;   // published by the bar.sync after staging
+      }
       mbar_wait(&accum_full[buf], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * acc_off + ((uint32_t)(q * 32) << 16);
@@ -407,8 +418,20 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       if (!(p.dbg & 1)) {
         int r = co_r0, cc = co_c0;
         while (r < rows_valid) {
-          const uint4 v = *reinterpret_cast<const uint4*>(c_s + r * p.cpitch + cc * 8);
-          *reinterpret_cast<uint4*>(C + (int64_t)(m0 + r) * p.ldc + n0 + cc * 8) = v;
+          uint4 v = *reinterpret_cast<const uint4*>(c_s + r * p.cpitch + cc * 8);
+          const int64_t orow = p.ss > 1 ? (int64_t)s_rowout[r] : (int64_t)(m0 + r);
+          uint4* gp = reinterpret_cast<uint4*>(C + orow * p.ldc + n0 + cc * 8);
+          if (p.accum) {
+            const uint4 o = *gp;
+            const uint32_t a4[4] = {v.x, v.y, v.z, v.w}, o4[4] = {o.x, o.y, o.z, o.w};
+            uint32_t r4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              r4[j] = pack_bf16x2(__uint_as_float(a4[j] << 16) + __uint_as_float(o4[j] << 16),
+                                  __uint_as_float(a4[j] & 0xffff0000u) + __uint_as_float(o4[j] & 0xffff0000u));
+            v = make_uint4(r4[0], r4[1], r4[2], r4[3]);
+          }
+          *gp = v;
           r += co_dr;
           cc += co_dc;
           if (cc >= cpr) { cc -= cpr; ++r; }
@@ -780,7 +803,8 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
 
 // y[M][Np] = x[M][Kp] * w[Np][Kp]^T  (all bf16, dense rows).  *handled = false -> caller uses the SIMT path.
 int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, int64_t Np, int64_t P_out,
-                  const int* gather /* nullptr | {stride, H, W, Ho, Wo} */,
+                  const int* gather /* nullptr | {stride, H, W, Ho, Wo}: A rows gathered */,
+                  const int* scatter /* nullptr | {stride, H, W, Ho, Wo, accumulate}: C rows scattered */,
                   double* stats, cudaStream_t stream, bool* handled) {
   *handled = false;
   static const bool off = getenv("X3D_PW_SIMT") != nullptr;      // A/B switch for tests and profiling
@@ -811,12 +835,19 @@ int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, 
     p.gs = gather[0]; p.gH = gather[1]; p.gW = gather[2]; p.gHo = gather[3]; p.gWo = gather[4];
     if ((M / ((int64_t)p.gHo * p.gWo)) * p.gH * p.gW >= (1ll << 31)) return 0;
   }
+  p.ss = 0; p.accum = 0;
+  if (scatter != nullptr && scatter[0] > 1) {
+    if (p.gs > 1 || stats != nullptr) return 0;
+    p.ss = scatter[0]; p.gH = scatter[1]; p.gW = scatter[2]; p.gHo = scatter[3]; p.gWo = scatter[4];
+    p.accum = scatter[5];
+    if ((M / ((int64_t)p.gHo * p.gWo)) * p.gH * p.gW >= (1ll << 31)) return 0;
+  }
   p.stages = BN > 128 ? 3 : 2;      // small-N layers: 2 stages so that 2-3 CTAs fit per SM (nk is 1-2 there)
   CUtensorMap mapA, mapB;
   if (!make_map_2d(&mapA, x, M, Kp, BM)) return 0;
   if (!make_map_2d(&mapB, w, Np, Kp, BN)) return 0;
   const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + (size_t)BN * BK * 2) + (size_t)BM * p.cpitch * 2 +
-                      (2 * p.stages + 6) * 8 + 16 + (size_t)2 * BN * 2 * sizeof(float) + 4096 + 16 + 512;
+                      (2 * p.stages + 6) * 8 + 16 + (size_t)2 * BN * 2 * sizeof(float) + 4096 + 16 + 1024;
   // resident CTAs: TMEM (512 columns per SM) and shared memory (227 KB per SM) bound the co-residency
   int per_sm = 512 / p.tmem_cols;
   const int by_smem = (int)((227 * 1024) / (smem + 1024));
