@@ -109,6 +109,9 @@ DW_CASES = [  # N, C, T, H, W, stride, kernel
     (2, 56, 2, 21, 35, 2, (3, 3, 3)),
     (1, 216, 2, 14, 14, 1, (3, 3, 3)),    # channel chunks that do not divide Cp evenly
     (2, 630, 2, 10, 10, 1, (3, 3, 3)),    # X3D-XL stage 4 (Cp = 632)
+    (2, 216, 3, 10, 10, 1, (3, 3, 3)),    # 158-pixel multigrid shape, stage 3 (narrow image: 4-wide tiles)
+    (2, 432, 2, 5, 5, 1, (3, 3, 3)),      # 158-pixel multigrid shape, stage 4
+    (2, 216, 2, 20, 20, 2, (3, 3, 3)),    # 158-pixel multigrid shape, stage 3 entry (20 -> 10)
 ]
 
 

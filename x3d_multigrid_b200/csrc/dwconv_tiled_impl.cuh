@@ -367,6 +367,8 @@ constexpr int kCC[3] = {48, 56, 72};
 template <int MODE>
 constexpr int tw_small() { return (MODE == M_FWD2) ? 4 : 8; }
 template <int MODE>
+constexpr int tw_tiny() { return 4; }   // narrow images (W = 4, 5, 10, 20 of the 112/158-pixel multigrid shapes)
+template <int MODE>
 constexpr int tw_big() { return (MODE == M_FWD2) ? 8 : 16; }
 
 // (Ho, Wo): extents of the produced tensor
@@ -386,8 +388,9 @@ TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW) {
   for (int ci = 0; ci < 3; ++ci) {
     const int CC = kCC[ci];
     const int nchunk = (Cp + CC - 1) / CC;
-    for (int twi = 0; twi < 2; ++twi) {
-      const int TW = twi ? tw_big<MODE>() : tw_small<MODE>();
+    for (int twi = 0; twi < 3; ++twi) {
+      const int TW = twi == 2 ? tw_tiny<MODE>() : twi ? tw_big<MODE>() : tw_small<MODE>();
+      if (twi == 2 && TW == tw_small<MODE>()) continue;
       if (TW % PW) continue;
       for (int TH = PH; TH <= 8; TH += PH) {
         const int patches = (TH / PH) * (TW / PW);
@@ -409,7 +412,7 @@ TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW) {
       }
     }
   }
-  if (best < 0.45) return p;    // too wasteful (exotic channel counts): let the direct kernel do it
+  if (best < 0.2) return p;     // too wasteful (exotic channel counts): let the direct kernel do it
   g.tiles_w = (Wo + p.TW - 1) / p.TW;
   const int tiles_h = (Ho + g.TH - 1) / g.TH;
   p.IH = M::in_ext(g.TH);
@@ -476,7 +479,7 @@ void launch_one(const TilePlan& p, const CUtensorMap& map, const Args& a, cudaSt
 template <typename T, int MODE, int PW>
 int launch_tiled(const TilePlan& p, const CUtensorMap& map, const Args& a, cudaStream_t stream) {
   constexpr bool DG = MODE >= 2;
-  constexpr int TWa = tw_small<MODE>(), TWb = tw_big<MODE>();
+  constexpr int TWa = tw_small<MODE>(), TWb = tw_big<MODE>(), TWc = tw_tiny<MODE>();
   const bool flag = DG ? (a.aux != nullptr) : (a.scale != nullptr);
 #define L2_(CCv, TWv)                                                               \
   do {                                                                              \
@@ -486,7 +489,8 @@ int launch_tiled(const TilePlan& p, const CUtensorMap& map, const Args& a, cudaS
 #define L_(CCv)                                    \
   if (p.CC == CCv) {                               \
     if (p.TW == TWa) L2_(CCv, TWa);                \
-    else L2_(CCv, TWb);                            \
+    else if (p.TW == TWb) L2_(CCv, TWb);           \
+    else L2_(CCv, TWc);                            \
     return 0;                                      \
   }
   L_(48) L_(56) L_(72)
@@ -698,7 +702,7 @@ int run_wgrad_tiled(const void* x, const void* dy, float* dw, int64_t N, int T_,
   CUtensorMap xmap, dymap;
   if (!make_input_map<T>(&xmap, x, N, T_, H, W, Cp, p.CC, p.IW, p.IH, scale != nullptr)) return 0;
   if (!make_input_map<T>(&dymap, dy, N, T_, Ho, Wo, Cp, p.CC, p.TW, p.g.TH, false)) return 0;
-  constexpr int TWa = tw_small<MODE>(), TWb = tw_big<MODE>();
+  constexpr int TWa = tw_small<MODE>(), TWb = tw_big<MODE>(), TWc = tw_tiny<MODE>();
   const bool xf = scale != nullptr;
   const int dse = (int)(dy_stage_bytes / esz);
 #define W2_(CCv, TWv)                                                                                             \
@@ -709,7 +713,8 @@ int run_wgrad_tiled(const void* x, const void* dy, float* dw, int64_t N, int T_,
 #define W_(CCv)                                    \
   if (p.CC == CCv) {                               \
     if (p.TW == TWa) W2_(CCv, TWa);                \
-    else W2_(CCv, TWb);                            \
+    else if (p.TW == TWb) W2_(CCv, TWb);           \
+    else W2_(CCv, TWc);                            \
     *handled = true;                               \
     return 0;                                      \
   }
