@@ -373,11 +373,22 @@ def main():
                  'gbs': v['bytes'] / 1e6 / v['ms'] if v['ms'] > 0 else None} for k, v in agg.items()}
     dom = max(agg, key=lambda k: agg[k]['ms']) if agg else None
     roofline = None
+    # measured DRAM traffic per launch of the dominant call: committed ncu summary (profiles/rNN_traffic.json, written by
+    # tools/summarize_profiles.py from an ncu dram-counter pass of this same command); null when it is for another kernel
+    traffic, traffic_src = None, None
+    try:
+        cand = sorted(f for f in os.listdir(os.path.join(ROOT, 'profiles')) if f.endswith('_traffic.json'))
+        if cand:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', cand[-1])))
+            if tj.get('call') == dom and args.version == 'M' and args.batch == 16 and args.crop == 224 and dtype == torch.bfloat16:
+                traffic, traffic_src = tj['dram_bytes_per_launch'], f'profiles/{cand[-1]} (ncu dram__bytes_read+write per launch)'
+    except Exception:
+        pass
     if dom:
         d = agg[dom]
         ach = d['bytes'] / 1e6 / d['ms']
         roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                    'frac': ach / hbm_peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                     'launches': d['n'], 'avg_launch_us': 1e3 * d['ms'] / d['n'],
                     'algorithmic_bytes_per_launch': d['bytes'] / d['n'],
                     'share_of_step': (d['ms'] / (3 if use_graph else args.steps)) / (ms / args.steps),

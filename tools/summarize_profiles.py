@@ -13,7 +13,8 @@ R = sys.argv[1] if len(sys.argv) > 1 else 'r01'
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, 'gpurun_out'), os.path.join(ROOT, 'profiles')
 os.makedirs(P, exist_ok=True)
-for name in ('bench.json', 'bench_reference.json', 'kernel_table.json', 'dw_microbench.json', 'pw_microbench.json', 'smi.csv'):
+for name in ('bench.json', 'bench_reference.json', 'kernel_table.json', 'dw_microbench.json', 'pw_microbench.json', 'smi.csv',
+             'multigrid_shapes.jsonl', 'bench_n2.json', 'bench_n4.json', 'bench_n8.json', 'fma_rate.txt'):
     src = os.path.join(G, f'{R}_{name}')
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, f'{R}_{name}'))
@@ -38,6 +39,27 @@ if os.path.exists(lc):
             f.write(f'"{k}",{n},{us:.1f},{us / tot:.4f}\n')
     with open(lc, 'rb') as fi, gzip.open(os.path.join(P, f'{R}_launches.csv.gz'), 'wb') as fo:
         shutil.copyfileobj(fi, fo)
+
+# ---- DRAM traffic of the dominant C-ABI call (x3d_dwconv_wgrad): ncu dram counters per launch, one eager step
+tc = os.path.join(G, f'{R}_dw_wgrad_traffic.csv')
+if os.path.exists(tc):
+    lines = [l for l in open(tc) if not l.startswith('==')]
+    per = collections.defaultdict(dict)
+    for row in csv.DictReader(lines):
+        v = float(row['Metric Value'].replace(',', ''))
+        u = row['Metric Unit']
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1.0, 'ms': 1e3}.get(u, 1.0)
+        per[row['ID']][row['Metric Name']] = v * scale
+    n = len(per)
+    rd = sum(d.get('dram__bytes_read.sum', 0.0) for d in per.values())
+    wr = sum(d.get('dram__bytes_write.sum', 0.0) for d in per.values())
+    us = sum(d.get('gpu__time_duration.sum', 0.0) for d in per.values())
+    with open(os.path.join(P, f'{R}_traffic.json'), 'w') as f:
+        json.dump({'call': 'x3d_dwconv_wgrad', 'kernels': 'dw3_wgrad_tiled_kernel<*> (all tiled launches of eager steps)',
+                   'launches': n, 'dram_read_bytes_per_launch': rd / n, 'dram_write_bytes_per_launch': wr / n,
+                   'dram_bytes_per_launch': (rd + wr) / n, 'avg_launch_us_under_ncu': us / n,
+                   'how': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:dw3_wgrad on bench.py --no-graph'},
+                  f, indent=1)
 
 # ---- ncu --set full captures -> small json of the metrics DESIGN.md / bench.py cite
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__registers_per_thread',

@@ -144,6 +144,7 @@ struct TileGeom {
   int T, Ho, Wo, Cp;     // extents of the tensor being PRODUCED (y for forward, dx for dgrad)
   int TH;                // output tile height (TW and CC are template parameters)
   int tiles_w;
+  int tiles_n;           // wgrad: number of samples (units = samples x spatial tiles)
   int stage_elems;       // ring-slot stride in elements (128-byte aligned)
 };
 
@@ -525,7 +526,7 @@ template <typename T, int MODE, int CC, int TW, int PW, bool XF>
 __global__ void __launch_bounds__(Cfg<PW>::MAXT, Cfg<PW>::MINB)
 dw3_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap dymap,
                        float* __restrict__ dw, const TileGeom g, const float* __restrict__ scale,
-                       const float* __restrict__ shift, int splits, int C, int dy_stage_elems) {
+                       const float* __restrict__ shift, int splits, int C, int dy_stage_elems, int nunits) {
   x3d::pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using M = Map<MODE>;                                           // forward geometry (MODE = M_FWD1 / M_FWD2)
@@ -543,15 +544,17 @@ dw3_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_co
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_red + 27 * CC);
 
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int ho0 = (blockIdx.x / g.tiles_w) * g.TH, wo0 = (blockIdx.x % g.tiles_w) * TW;
   const int cbase = blockIdx.y * CC;
-  const int n = blockIdx.z;
   const int pair = tid % PAIRS, patch = tid / PAIRS;
   const int py = patch / PPR, px = patch % PPR;
   const int c = cbase + 2 * pair;
   const bool ch_ok = c < Cp;
-  const int hi0 = M::in_org(ho0), wi0 = M::in_org(wo0);
   const int nT = g.T;
+  // PERSISTENT over work units (sample n, spatial tile): the 27 x 2 weight-gradient accumulators live in registers
+  // across units, so the block reduction and the global fp32 reds (all CTAs of a channel chunk hit the same
+  // C x 27 addresses, and same-address reds serialise in L2) happen once per CTA instead of once per tile.
+  const int tiles_per_n = nunits / g.tiles_n;                    // spatial tiles per sample
+  int n = 0, ho0 = 0, wo0 = 0, hi0 = 0, wi0 = 0;
   const uint32_t x_bytes = (uint32_t)(IH * ROW * sizeof(T));
   const uint32_t dy_bytes = (uint32_t)(g.TH * TW * CC * sizeof(T));
 
@@ -571,18 +574,7 @@ dw3_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_co
     if (hx) tma_load_5d(xbuf + slot * g.stage_elems, &xmap, &full_bar[slot], cbase, wi0, hi0, s, n);
     if (hd) tma_load_5d(dbuf + slot * dy_stage_elems, &dymap, &full_bar[slot], cbase, wo0, ho0, s + 1, n);
   };
-  if (tid == 0) {
-#pragma unroll
-    for (int k = 0; k < NSTAGE - 1; ++k)
-      if (k - 1 < nT) issue(k - 1, k);
-  }
-
   float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
-  if (XF && ch_ok) {
-    const int b = n % splits;
-    sc = *reinterpret_cast<const float2*>(scale + (int64_t)b * Cp + c);
-    sh = *reinterpret_cast<const float2*>(shift + (int64_t)b * Cp + c);
-  }
   const int win_base = (M::win_off(py * PH) * IW + M::win_off(px * PW)) * CC + 2 * pair;
   const int dy_base = ((py * PH) * TW + px * PW) * CC + 2 * pair;
 
@@ -590,8 +582,6 @@ dw3_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_co
 #pragma unroll
   for (int k = 0; k < 27; ++k) gacc[k] = make_float2(0.f, 0.f);
   float2 dyA[NO], dyB[NO], dyC[NO];
-#pragma unroll
-  for (int o = 0; o < NO; ++o) dyA[o] = dyB[o] = dyC[o] = make_float2(0.f, 0.f);
 
   int slot = 0;
   uint32_t parity = 0;
@@ -647,16 +637,41 @@ dw3_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_co
     }
   };
 
-  // steps -1, 0, ..., T-1 with the dy register sets rotating (A,B,C) -> (C,A,B) -> (B,C,A)
-  int s = -1;
-  for (; s + 3 <= nT; s += 3) {
-    step(s, dyA, dyB, dyC);
-    step(s + 1, dyC, dyA, dyB);
-    step(s + 2, dyB, dyC, dyA);
-  }
-  if (s < nT) {
-    step(s, dyA, dyB, dyC);
-    if (s + 1 < nT) step(s + 1, dyC, dyA, dyB);
+  for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    n = unit / tiles_per_n;
+    const int tile = unit - n * tiles_per_n;
+    ho0 = (tile / g.tiles_w) * g.TH;
+    wo0 = (tile % g.tiles_w) * TW;
+    hi0 = M::in_org(ho0);
+    wi0 = M::in_org(wo0);
+    // the ring slots the first loads of this unit go to were last read two / three steps ago (all threads passed
+    // the barrier of the previous unit's final step since), so the pipeline restarts without another barrier
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < NSTAGE - 1; ++k) {
+        int sl = slot + k;
+        if (sl >= NSTAGE) sl -= NSTAGE;
+        if (k - 1 < nT) issue(k - 1, sl);
+      }
+    }
+    if (XF && ch_ok) {
+      const int b = n % splits;
+      sc = *reinterpret_cast<const float2*>(scale + (int64_t)b * Cp + c);
+      sh = *reinterpret_cast<const float2*>(shift + (int64_t)b * Cp + c);
+    }
+#pragma unroll
+    for (int o = 0; o < NO; ++o) dyA[o] = dyB[o] = dyC[o] = make_float2(0.f, 0.f);
+    // steps -1, 0, ..., T-1 with the dy register sets rotating (A,B,C) -> (C,A,B) -> (B,C,A)
+    int s = -1;
+    for (; s + 3 <= nT; s += 3) {
+      step(s, dyA, dyB, dyC);
+      step(s + 1, dyC, dyA, dyB);
+      step(s + 2, dyB, dyC, dyA);
+    }
+    if (s < nT) {
+      step(s, dyA, dyB, dyC);
+      if (s + 1 < nT) step(s + 1, dyC, dyA, dyB);
+    }
   }
 
   // ---- reduction: patches of the CTA -> shared, CTA -> global ------------------------------------
@@ -685,7 +700,19 @@ void launch_wgrad_one(const TilePlan& p, const CUtensorMap& xmap, const CUtensor
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  x3d::launch(kfn, p.grid, p.threads, smem, stream, xmap, dymap, dw, p.g, scale, shift, splits, C, dy_stage_elems);
+  // persistent grid: as many CTAs per channel chunk as fit the 2 x 148 resident slots, each walking
+  // ceil(units / CTAs) (sample, tile) units
+  const int nunits = (int)(p.grid.x * p.grid.z);
+  const int chunks = (int)p.grid.y;
+  int gx = (2 * kNumSMs) / chunks;
+  if (gx < 1) gx = 1;
+  if (gx > nunits) gx = nunits;
+  const int per = (nunits + gx - 1) / gx;
+  gx = (nunits + per - 1) / per;                       // same number of rounds, no idle CTAs
+  TileGeom g = p.g;
+  g.tiles_n = (int)p.grid.z;
+  x3d::launch(kfn, dim3((unsigned)gx, (unsigned)chunks, 1u), p.threads, smem, stream, xmap, dymap, dw, g, scale, shift, splits,
+              C, dy_stage_elems, nunits);
 }
 
 // x: [N][T_][H][W][Cp] (conv input), dy: [N][T_][Ho][Wo][Cp]
