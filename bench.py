@@ -380,8 +380,10 @@ def main():
         cand = sorted(f for f in os.listdir(os.path.join(ROOT, 'profiles')) if f.endswith('_traffic.json'))
         if cand:
             tj = json.load(open(os.path.join(ROOT, 'profiles', cand[-1])))
-            if tj.get('call') == dom and args.version == 'M' and args.batch == 16 and args.crop == 224 and dtype == torch.bfloat16:
-                traffic, traffic_src = tj['dram_bytes_per_launch'], f'profiles/{cand[-1]} (ncu dram__bytes_read+write per launch)'
+            tc = tj.get('calls', {}).get(dom)
+            if tc and args.version == 'M' and args.batch == 16 and args.frames == 16 and args.crop == 224 and dtype == torch.bfloat16:
+                traffic = tc['dram_bytes_per_launch']
+                traffic_src = f'profiles/{cand[-1]} (ncu dram__bytes_read+write, mean over the tiled launches of {dom})'
     except Exception:
         pass
     if dom:

@@ -40,26 +40,37 @@ if os.path.exists(lc):
     with open(lc, 'rb') as fi, gzip.open(os.path.join(P, f'{R}_launches.csv.gz'), 'wb') as fo:
         shutil.copyfileobj(fi, fo)
 
-# ---- DRAM traffic of the dominant C-ABI call (x3d_dwconv_wgrad): ncu dram counters per launch, one eager step
-tc = os.path.join(G, f'{R}_dw_wgrad_traffic.csv')
+# ---- DRAM traffic of the depthwise C-ABI calls: ncu dram counters per launch over eager steps
+tc = os.path.join(G, f'{R}_dw_traffic.csv')
 if os.path.exists(tc):
+    import re
     lines = [l for l in open(tc) if not l.startswith('==')]
     per = collections.defaultdict(dict)
     for row in csv.DictReader(lines):
         v = float(row['Metric Value'].replace(',', ''))
-        u = row['Metric Unit']
-        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1.0, 'ms': 1e3}.get(u, 1.0)
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1.0, 'ms': 1e3}.get(row['Metric Unit'], 1.0)
         per[row['ID']][row['Metric Name']] = v * scale
-    n = len(per)
-    rd = sum(d.get('dram__bytes_read.sum', 0.0) for d in per.values())
-    wr = sum(d.get('dram__bytes_write.sum', 0.0) for d in per.values())
-    us = sum(d.get('gpu__time_duration.sum', 0.0) for d in per.values())
+        per[row['ID']]['kernel'] = row['Kernel Name']
+    calls = collections.defaultdict(list)
+    for d in per.values():
+        k = d['kernel']
+        if 'dw3_wgrad' in k:
+            calls['x3d_dwconv_wgrad'].append(d)
+        else:
+            m = re.search(r'dw3_tiled_kernel<[^,]+, (\d)', k)
+            if m:
+                calls['x3d_dwconv_fwd' if int(m.group(1)) < 2 else 'x3d_dwconv_dgrad'].append(d)
+    out = {'how': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:dw3_ on bench.py --no-graph (tiled 3x3x3 '
+                  'kernels; the 5x1x1 stem conv of each call runs the direct kernel and is not in this set)', 'calls': {}}
+    for call, ds in calls.items():
+        n = len(ds)
+        rd = sum(d.get('dram__bytes_read.sum', 0.0) for d in ds)
+        wr = sum(d.get('dram__bytes_write.sum', 0.0) for d in ds)
+        us = sum(d.get('gpu__time_duration.sum', 0.0) for d in ds)
+        out['calls'][call] = {'launches': n, 'dram_read_bytes_per_launch': rd / n, 'dram_write_bytes_per_launch': wr / n,
+                              'dram_bytes_per_launch': (rd + wr) / n, 'avg_launch_us_under_ncu': us / n}
     with open(os.path.join(P, f'{R}_traffic.json'), 'w') as f:
-        json.dump({'call': 'x3d_dwconv_wgrad', 'kernels': 'dw3_wgrad_tiled_kernel<*> (all tiled launches of eager steps)',
-                   'launches': n, 'dram_read_bytes_per_launch': rd / n, 'dram_write_bytes_per_launch': wr / n,
-                   'dram_bytes_per_launch': (rd + wr) / n, 'avg_launch_us_under_ncu': us / n,
-                   'how': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:dw3_wgrad on bench.py --no-graph'},
-                  f, indent=1)
+        json.dump(out, f, indent=1)
 
 # ---- ncu --set full captures -> small json of the metrics DESIGN.md / bench.py cite
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__registers_per_thread',
