@@ -19,6 +19,11 @@ int dwconv_dgrad_tiled(const void* dy, const float* w_packed, void* dx, int64_t 
 int dwconv_wgrad_tiled(const void* x, const void* dy, float* dw, int64_t N, int64_t T, int64_t H, int64_t W,
                        int64_t C, int64_t Cp, int stride, const float* in_scale, const float* in_shift, int splits,
                        int relu_in, x3d_dtype_t dt, cudaStream_t stream, bool* handled);
+// dwconv_temporal.cu: kt x 1 x 1 streaming kernels (stem conv1_t)
+int dwconv_temporal(const void* x, const float* w_packed, void* y, int64_t N, int64_t T_, int64_t P, int64_t Cp, int kt,
+                    int flip, double* stats, x3d_dtype_t dt, cudaStream_t stream, bool* handled);
+int dwconv_temporal_wgrad(const void* x, const void* dy, float* dw, int64_t N, int64_t T_, int64_t P, int64_t C,
+                          int64_t Cp, int kt, x3d_dtype_t dt, cudaStream_t stream, bool* handled);
 }
 
 struct DwGeom {
@@ -139,6 +144,14 @@ extern "C" int x3d_dwconv_fwd(const void* x, const float* w_packed, void* y, int
   g.Ho = (int)((H + 2 * (kh / 2) - kh) / stride + 1);
   g.Wo = (int)((W + 2 * (kw / 2) - kw) / stride + 1);
   if (N * T_ * g.Ho * g.Wo == 0) return 0;
+  if (kt == 5 && stride == 1 && in_scale == nullptr) {      // stem conv1_t: streaming temporal kernel
+    bool handled = false;
+    int rc = dwconv_temporal(x, w_packed, y, N, T_, H * W, Cp, kt, 0, stats, dt, as_stream(stream), &handled);
+    if (handled) {
+      if (rc == 0) X3D_LAUNCH_CHECK();
+      return rc;
+    }
+  }
   if (kt == 3) {
     bool handled = false;
     int rc = dwconv_fwd_tiled(x, w_packed, y, N, T_, H, W, Cp, stride, in_scale, in_shift, splits, relu_in, stats, dt,
@@ -248,6 +261,14 @@ extern "C" int x3d_dwconv_dgrad(const void* dy, const float* w_packed, void* dx,
   g.Wo = (int)((W + 2 * (kw / 2) - kw) / stride + 1);
   const int64_t P = T_ * H * W;
   if (N * P == 0) return 0;
+  if (kt == 5 && stride == 1 && mask_src == nullptr) {
+    bool handled = false;
+    int rc = dwconv_temporal(dy, w_packed, dx, N, T_, H * W, Cp, kt, 1, nullptr, dt, as_stream(stream), &handled);
+    if (handled) {
+      if (rc == 0) X3D_LAUNCH_CHECK();
+      return rc;
+    }
+  }
   if (kt == 3) {
     bool handled = false;
     int rc = dwconv_dgrad_tiled(dy, w_packed, dx, N, T_, H, W, Cp, stride, mask_src, mask_scale, mask_shift, splits,
@@ -361,6 +382,14 @@ extern "C" int x3d_dwconv_wgrad(const void* x, const void* dy, float* dw, int64_
   g.Wo = (int)((W + 2 * (kw / 2) - kw) / stride + 1);
   const int64_t P = T_ * g.Ho * g.Wo;
   if (N * P == 0) return 0;
+  if (kt == 5 && stride == 1 && in_scale == nullptr) {
+    bool handled = false;
+    int rc = dwconv_temporal_wgrad(x, dy, dw, N, T_, H * W, C, Cp, kt, dt, as_stream(stream), &handled);
+    if (handled) {
+      if (rc == 0) X3D_LAUNCH_CHECK();
+      return rc;
+    }
+  }
   if (kt == 3) {
     bool handled = false;
     int rc = dwconv_wgrad_tiled(x, dy, dw, N, T_, H, W, C, Cp, stride, in_scale, in_shift, splits, relu_in, dt,
