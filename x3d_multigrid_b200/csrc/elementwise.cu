@@ -996,32 +996,48 @@ __global__ void skinny_gemm_kcontig_kernel(const float* __restrict__ A, int64_t 
                                            int M, int Nn, int K, const float* __restrict__ bias, int relu,
                                            const float* __restrict__ mul, int accumulate) {
   x3d::pdl_prologue();
+  // one warp per JW output columns: the MR values of A for a k are loaded once and feed JW x MR FMAs
+  constexpr int JW = MR <= 16 ? 4 : 2;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
-  if (warp >= Nn) return;
-  const int j = warp;
-  float acc[MR];
+  const int j0 = warp * JW;
+  if (j0 >= Nn) return;
+  float acc[JW][MR];
 #pragma unroll
-  for (int i = 0; i < MR; ++i) acc[i] = 0.f;
+  for (int q = 0; q < JW; ++q)
+#pragma unroll
+    for (int i = 0; i < MR; ++i) acc[q][i] = 0.f;
   for (int k = lane; k < K; k += 32) {
-    const float b = B[(int64_t)j * sbj + k];
+    float a[MR], b[JW];
 #pragma unroll
-    for (int i = 0; i < MR; ++i)
-      if (i < M) acc[i] = fmaf(A[(int64_t)i * sai + (int64_t)k * sak], b, acc[i]);
+    for (int q = 0; q < JW; ++q) b[q] = (j0 + q < Nn) ? B[(int64_t)(j0 + q) * sbj + k] : 0.f;
+#pragma unroll
+    for (int i = 0; i < MR; ++i) a[i] = (i < M) ? A[(int64_t)i * sai + (int64_t)k * sak] : 0.f;
+#pragma unroll
+    for (int q = 0; q < JW; ++q)
+#pragma unroll
+      for (int i = 0; i < MR; ++i) acc[q][i] = fmaf(a[i], b[q], acc[q][i]);
   }
 #pragma unroll
-  for (int i = 0; i < MR; ++i) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-  }
-  if (lane == 0) {
+  for (int q = 0; q < JW; ++q)
 #pragma unroll
     for (int i = 0; i < MR; ++i) {
-      if (i < M) {
-        float v = acc[i] + (bias ? bias[j] : 0.f);
-        if (relu) v = fmaxf(v, 0.f);
-        if (mul) v *= mul[(int64_t)i * Nn + j];
-        float* dst = &C[(int64_t)i * ldc + j];
-        *dst = accumulate ? (*dst + v) : v;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], o);
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < JW; ++q) {
+      const int j = j0 + q;
+      if (j >= Nn) break;
+#pragma unroll
+      for (int i = 0; i < MR; ++i) {
+        if (i < M) {
+          float v = acc[q][i] + (bias ? bias[j] : 0.f);
+          if (relu) v = fmaxf(v, 0.f);
+          if (mul) v *= mul[(int64_t)i * Nn + j];
+          float* dst = &C[(int64_t)i * ldc + j];
+          *dst = accumulate ? (*dst + v) : v;
+        }
       }
     }
   }
@@ -1056,7 +1072,7 @@ extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const fl
                               const float* mul, int accumulate, x3d_stream_t stream) {
   if (M == 0 || Nn == 0) return 0;
   if (M <= 32 && sbk == 1) {
-    const int64_t threads = Nn * 32;
+    const int64_t threads = cdiv(Nn, M <= 16 ? 4 : 2) * 32;     // JW columns per warp
 #define SK_(MR) x3d::launch(skinny_gemm_kcontig_kernel<MR>, (unsigned)cdiv(threads, 256), 256, 0, as_stream(stream),  \
       A, sai, sak, B, sbj, C, ldc, (int)M, (int)Nn, (int)K, bias, relu, mul, accumulate)
     if (M <= 8) SK_(8); else if (M <= 16) SK_(16); else SK_(32);
