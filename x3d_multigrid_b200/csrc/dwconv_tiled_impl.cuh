@@ -123,6 +123,26 @@ __device__ __forceinline__ float2 ldg_pair_if<float>(const float* p, uint32_t pr
                : "l"(p), "r"(pred));
   return v;
 }
+// raw variants: the loaded register(s) are NOT touched at the load site, so the scoreboard wait happens where the
+// value is finally unpacked (the store phase), not right behind the load
+template <typename T> struct RawPair;
+template <> struct RawPair<__nv_bfloat16> { uint32_t w; };
+template <> struct RawPair<float> { float2 v; };
+__device__ __forceinline__ RawPair<__nv_bfloat16> ldg_raw_if(const __nv_bfloat16* p, uint32_t pred) {
+  RawPair<__nv_bfloat16> r;
+  r.w = 0;
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p ld.global.nc.b32 %0, [%1];\n}\n" : "+r"(r.w) : "l"(p), "r"(pred));
+  return r;
+}
+__device__ __forceinline__ RawPair<float> ldg_raw_if(const float* p, uint32_t pred) {
+  RawPair<float> r;
+  r.v = ldg_pair_if<float>(p, pred);
+  return r;
+}
+__device__ __forceinline__ float2 unpack_raw(RawPair<__nv_bfloat16> r) {
+  return make_float2(__uint_as_float(r.w << 16), __uint_as_float(r.w & 0xffff0000u));
+}
+__device__ __forceinline__ float2 unpack_raw(RawPair<float> r) { return r.v; }
 // predicated store of a channel pair; returns the values as stored (for the statistics)
 template <typename T>
 __device__ __forceinline__ float2 st_pair_if(T* p, float2 v, uint32_t pred);
@@ -230,7 +250,7 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
   const int64_t out0 = ((int64_t)n * nT * g.Ho + ho_t) * (int64_t)orow + (int64_t)wo_t * Cp + c;   // plane 0
   T* yp = y + out0;
   const T* ap = AUX ? aux + out0 : nullptr;
-  float2 av[NO];                           // aux values of the plane stored next (dgrad epilogue)
+  RawPair<T> av[NO];                       // aux values (raw) of the plane stored next (dgrad epilogue)
 
   // store a finished accumulator as the next output plane (planes are finished in order 0,1,2,...)
   auto store_plane = [&](float2 (&a)[NO]) {
@@ -241,15 +261,17 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
         const int o = oy * PW + ox;
         const uint32_t ok = omask & (1u << o);
         float2 v = a[o];
+        float2 ax = make_float2(0.f, 0.f);
         if (AUX) {                          // d = dgrad * [relu(bn(aux)) > 0]
-          const float2 t = __ffma2_rn(av[o], sc, sh);
+          ax = unpack_raw(av[o]);
+          const float2 t = __ffma2_rn(ax, sc, sh);
           v.x = t.x > 0.f ? v.x : 0.f;
           v.y = t.y > 0.f ? v.y : 0.f;
         }
         float2 r = st_pair_if<T>(yp + oy * orow + ox * Cp, v, ok);
         if (!ok) r = make_float2(0.f, 0.f);
         ssum.x += r.x; ssum.y += r.y;
-        ssq = __ffma2_rn(r, AUX ? av[o] : r, ssq);
+        ssq = __ffma2_rn(r, AUX ? ax : r, ssq);
         a[o] = make_float2(0.f, 0.f);
       }
     }
@@ -261,7 +283,7 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
       for (int oy = 0; oy < PH; ++oy)
 #pragma unroll
         for (int ox = 0; ox < PW; ++ox)
-          av[oy * PW + ox] = ldg_pair_if<T>(ap + oy * orow + ox * Cp, omask & (1u << (oy * PW + ox)));
+          av[oy * PW + ox] = ldg_raw_if(ap + oy * orow + ox * Cp, omask & (1u << (oy * PW + ox)));
       ap += out_plane;
     }
   };
