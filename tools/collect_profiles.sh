@@ -20,8 +20,8 @@ ncu --set full --clock-control none --import-source on -k regex:dw3_ -s 9 -c 3 -
     python tools/dw_microbench.py --layer l1.0 --iters 3 > gpurun_out/ncu_dw.log 2>&1
 echo "ncu dw rc=$?"
 # DRAM traffic of the depthwise C-ABI calls (tiled kernels dw3_*: fwd / dgrad / wgrad), eager steps
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:dw3_wgrad \
-    -c 200 --csv --log-file gpurun_out/${R}_dw_wgrad_traffic.csv \
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:dw3_ \
+    -c 400 --csv --log-file gpurun_out/${R}_dw_traffic.csv \
     python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_traffic.log 2>&1
 echo "ncu traffic rc=$?"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/${R}_smi.csv
