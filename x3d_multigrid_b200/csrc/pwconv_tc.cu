@@ -2,16 +2,20 @@
 //
 //   C[m][n] = sum_k A[m][k] * B[n][k]      A: activations [M][Kp] (NDHWC rows), B: weights [Np][Kp]
 //
-// One CTA per 128 x BN output tile (BN = whole N up to 256, else N split in equal parts), 6 warps:
-//   warp 0  : TMA producer  -- per 64-wide K chunk one box of A (128 x 64) and one of B (BN x 64) into a
-//             4-stage shared-memory ring (SWIZZLE_128B), completion on "full" mbarriers;
+// Persistent CTAs (2-3 per SM), each walking a contiguous range of 128-row tiles of one BN <= 128 wide column part;
+// 6 warps:
+//   warp 0  : producer -- TMA boxes of A (128 x 64) and B (BN x 64) per 64-wide K chunk into a 2-3 stage shared
+//             ring (SWIZZLE_128B, "full" mbarriers); when the A rows are narrower than 128 bytes (K < 64) the
+//             whole warp copies the tile with coalesced 16-byte cp.async into the same swizzled layout instead
+//             (TMA retires only ~1 box row per 20 cycles) and B stays resident; strided (downsample) convs gather
+//             their input rows here;
 //   warp 1  : allocates TMEM, then one elected thread issues tcgen05.mma.cta_group::1.kind::f16
-//             (M=128, N=BN, K=16) per 16-wide K step, tcgen05.commit frees the ring slot ("empty") and
-//             finally signals the accumulator ("accum") to the epilogue;
-//   warps 2-5: epilogue -- tcgen05.ld of their 32 TMEM lanes (= 32 output rows), bf16 pack, 16-byte
-//             global stores, and (forward) the per-sample column sums / sums of squares that feed the
-//             following SubBatchNorm3d: a 5-step butterfly transpose-reduce across the warp (1 shuffle
-//             per column instead of 5), shared-memory merge of the 4 warps, one fp64 atomic per column.
+//             (M=128, N=BN, K=16) per 16-wide K step into one of two TMEM accumulators, tcgen05.commit frees the
+//             ring slot ("empty") and finally signals the accumulator ("accum_full") to the epilogue;
+//   warps 2-5: epilogue -- tcgen05.ld of their 32 TMEM lanes (= 32 output rows), bf16 pack into a padded shared
+//             staging tile, coalesced 16-byte global stores (optionally scattered / accumulated: dgrad of a
+//             strided conv), and (forward) the per-sample column sums / sums of squares that feed the following
+//             SubBatchNorm3d, kept in registers across the CTA's tiles and flushed once per sample.
 // K and N of this network are small (24..432) and M is huge: every layer is HBM-bound,
 // so the design goal is simply to stream A and C at full bandwidth with several CTAs in flight per SM.
 #include <cuda.h>
@@ -22,7 +26,7 @@ using namespace x3d;
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BK = 64;
 constexpr int NTHREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,48 +116,6 @@ struct TcParams {
   long long P_out;
 };
 
-// 16 values per lane (row = lane) -> each lane ends with the sum over the 32 rows of column
-// ((lane>>1) & 15); 16 shuffles instead of 80.
-__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
-  {
-    const bool up = lane & 16;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float send = up ? v[j] : v[j + 8];
-      const float keep = up ? v[j + 8] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool up = lane & 8;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float send = up ? v[j] : v[j + 4];
-      const float keep = up ? v[j + 4] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool up = lane & 4;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float send = up ? v[j] : v[j + 2];
-      const float keep = up ? v[j + 2] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-  }
-  {
-    const bool up = lane & 2;
-    const float send = up ? v[0] : v[1];
-    const float keep = up ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-// column (0..15) whose total a lane holds after butterfly16
-__device__ __forceinline__ int butterfly_col(int lane) {
-  return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-}
 
 // Persistent kernel: grid = (min(tiles_m, resident CTAs), column parts).  Each CTA walks its 128-row tiles;
 // the three roles run as independent pipelines connected by mbarriers:
@@ -853,7 +815,8 @@ int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, 
   const int by_smem = (int)((227 * 1024) / (smem + 1024));
   if (per_sm > by_smem) per_sm = by_smem;
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 3) per_sm = 3;
+  static const int per_sm_cap = getenv("X3D_TC_PERSM") ? atoi(getenv("X3D_TC_PERSM")) : 3;
+  if (per_sm > per_sm_cap) per_sm = per_sm_cap;
   const int parts_n = (int)((Np + BN - 1) / BN);
   int gx = (kNumSMs * per_sm) / parts_n;
   if (gx < 1) gx = 1;
