@@ -166,18 +166,27 @@ struct TileGeom {
   int tiles_w;
   int tiles_n;           // wgrad: number of samples (units = samples x spatial tiles)
   int stage_elems;       // ring-slot stride in elements (128-byte aligned)
+  int aux_stage_elems;   // stride-2 dgrad: aux-tile ring-slot stride in elements
 };
 
 // XF: fused relu(x*scale+shift) on the staged input (forward modes)
 // AUX: dgrad epilogue with the ReLU mask / BN sums from the saved conv1 output
 template <typename T, int MODE, int CC, int TW, int PW, bool XF, bool AUX>
 __global__ void __launch_bounds__(Cfg<PW>::MAXT, Cfg<PW>::MINB)
-dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ w, T* __restrict__ y,
+dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap amap,
+                 const float* __restrict__ w, T* __restrict__ y,
                  const TileGeom g, const float* __restrict__ scale, const float* __restrict__ shift, int splits,
                  const T* __restrict__ aux, double* __restrict__ stats) {
   x3d::pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using M = Map<MODE>;
+  // Stride-2 dgrad does only 6.75 FMA per output: its plane time is about one global-load latency, and the per-thread
+  // aux loads (issued at the start of a plane, needed at its end) were 55 % of its stall samples (ncu).  For that
+  // mapping the aux tile of output plane t rides the TMA ring together with input plane t (ring of 4, look-ahead 2)
+  // and is read from shared memory one call later.
+  constexpr bool AUXT = AUX && MODE == M_DG2;
+  constexpr int NSTAGE = AUXT ? 4 : 3;
+  constexpr int LOOK = AUXT ? 2 : NSTAGE - 1;                    // planes of TMA look-ahead
   constexpr int WR = M::in_ext(PH), WC = M::in_ext(PW);         // per-thread input window
   constexpr int IW = M::in_ext(TW);                              // CTA input tile width (with halo)
   constexpr int ROW = IW * CC;                                   // smem row stride (elements)
@@ -187,7 +196,8 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
   const int IH = M::in_ext(g.TH);
   const int Cp = g.Cp;
   T* const sbuf = reinterpret_cast<T*>(smem_raw);               // NSTAGE plane buffers (ring)
-  float* s_stat = reinterpret_cast<float*>(sbuf + NSTAGE * g.stage_elems);
+  T* const abuf = sbuf + NSTAGE * g.stage_elems;                // AUXT: NSTAGE aux tiles [TH][TW][CC]
+  float* s_stat = reinterpret_cast<float*>(abuf + (AUXT ? NSTAGE * g.aux_stage_elems : 0));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stat + 2 * CC);
 
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -210,13 +220,15 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
   }
   __syncthreads();
   x3d::pdl_wait();                         // on-chip setup done; global memory is touched only from here on
-  auto issue = [&](int t, int slot) {      // one thread: arm the barrier, fire one TMA box load
-    mbar_expect_tx(&full_bar[slot], plane_bytes);
+  const uint32_t aux_bytes = AUXT ? (uint32_t)(g.TH * TW * CC * sizeof(T)) : 0u;
+  auto issue = [&](int t, int slot) {      // one thread: arm the barrier, fire the TMA box load(s) of plane t
+    mbar_expect_tx(&full_bar[slot], plane_bytes + aux_bytes);
     tma_load_5d(sbuf + slot * g.stage_elems, &tmap, &full_bar[slot], cbase, wi0, hi0, t, n);
+    if (AUXT) tma_load_5d(abuf + slot * g.aux_stage_elems, &amap, &full_bar[slot], cbase, wo0, ho0, t, n);
   };
   if (tid == 0) {
 #pragma unroll
-    for (int k = 0; k < NSTAGE - 1; ++k)
+    for (int k = 0; k < LOOK; ++k)
       if (k < nT) issue(k, k);
   }
 
@@ -250,7 +262,9 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
   const int64_t out0 = ((int64_t)n * nT * g.Ho + ho_t) * (int64_t)orow + (int64_t)wo_t * Cp + c;   // plane 0
   T* yp = y + out0;
   const T* ap = AUX ? aux + out0 : nullptr;
-  RawPair<T> av[NO];                       // aux values (raw) of the plane stored next (dgrad epilogue)
+  RawPair<T> av[NO];                       // aux values (raw) of the plane stored next (dgrad epilogue, register path)
+  const T* aslot = abuf;                   // AUXT: aux tile of the plane stored next
+  const int aux_base = ((py * PH) * TW + px * PW) * CC + 2 * pair;
 
   // store a finished accumulator as the next output plane (planes are finished in order 0,1,2,...)
   auto store_plane = [&](float2 (&a)[NO]) {
@@ -263,7 +277,7 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
         float2 v = a[o];
         float2 ax = make_float2(0.f, 0.f);
         if (AUX) {                          // d = dgrad * [relu(bn(aux)) > 0]
-          ax = unpack_raw(av[o]);
+          ax = AUXT ? lds_pair<T>(aslot + aux_base + (oy * TW + ox) * CC) : unpack_raw(av[o]);
           const float2 t = __ffma2_rn(ax, sc, sh);
           v.x = t.x > 0.f ? v.x : 0.f;
           v.y = t.y > 0.f ? v.y : 0.f;
@@ -278,7 +292,7 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     yp += out_plane;
   };
   auto load_aux = [&]() {
-    if (AUX) {
+    if (AUX && !AUXT) {
 #pragma unroll
       for (int oy = 0; oy < PH; ++oy)
 #pragma unroll
@@ -296,13 +310,18 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     mbar_wait(&full_bar[slot], parity);    // TMA bytes of plane tin have landed
     __syncthreads();                       // everybody is done with plane tin-1: its ring slot is free
     if (tid == 0) {
-      const int tn = tin + NSTAGE - 1;
-      int sn = slot + NSTAGE - 1;
+      const int tn = tin + LOOK;
+      int sn = slot + LOOK;
       if (sn >= NSTAGE) sn -= NSTAGE;
       if (tn < nT) issue(tn, sn);
     }
     if (tin >= 1) load_aux();              // aux of output plane tin-1, consumed after the FMA phase
     const T* bp = sbuf + slot * g.stage_elems + win_base;
+    if (AUXT) {                            // aux of output plane tin-1 sits in the previous slot (still intact)
+      int ps = slot - 1;
+      if (ps < 0) ps += NSTAGE;
+      aslot = abuf + ps * g.aux_stage_elems;
+    }
     if (++slot == NSTAGE) { slot = 0; parity ^= 1u; }
 #pragma unroll
     for (int r = 0; r < WR; ++r) {
@@ -344,18 +363,28 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
     plane(tin + 2, accB, accC, accA);
   }
   // remainder; the last executed plane's `md` accumulator holds output plane T-1
+  auto final_aux = [&]() {                 // AUXT: aux[T-1] arrived with input plane T-1 = the slot before `slot`
+    if (AUXT) {
+      int ps = slot - 1;
+      if (ps < 0) ps += NSTAGE;
+      aslot = abuf + ps * g.aux_stage_elems;
+    }
+  };
   const int rem = nT - tin;
   if (rem == 0) {
     load_aux();
+    final_aux();
     store_plane(accC);                     // last call was plane(.., accB, accC, accA): md = accC
   } else if (rem == 1) {
     plane(tin, accA, accB, accC);
     load_aux();
+    final_aux();
     store_plane(accB);
   } else {
     plane(tin, accA, accB, accC);
     plane(tin + 1, accC, accA, accB);
     load_aux();
+    final_aux();
     store_plane(accA);
   }
 
@@ -443,7 +472,11 @@ TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW) {
   const size_t plane_bytes = (size_t)p.IH * p.IW * p.CC * esz;
   const size_t stage_bytes = (plane_bytes + 127) / 128 * 128;
   g.stage_elems = (int)(stage_bytes / esz);
-  p.smem = NSTAGE * stage_bytes + (size_t)p.CC * 2 * sizeof(float) + NSTAGE * sizeof(uint64_t) + 16;
+  // stride-2 dgrad with the mask epilogue: 4 ring slots, each with an aux tile [TH][TW][CC] (sized for that case always)
+  const size_t aux_stage_bytes = MODE == M_DG2 ? ((size_t)g.TH * p.TW * p.CC * esz + 127) / 128 * 128 : 0;
+  g.aux_stage_elems = (int)(aux_stage_bytes / esz);
+  p.smem = (NSTAGE + 1) * stage_bytes + 4 * aux_stage_bytes + (size_t)p.CC * 2 * sizeof(float) +
+           (NSTAGE + 1) * sizeof(uint64_t) + 16;
   p.grid = dim3((unsigned)(g.tiles_w * tiles_h), (unsigned)((Cp + p.CC - 1) / p.CC), (unsigned)N);
   if (N > 65535 || (int64_t)Ho * Wo * Cp >= (1ll << 31)) return p;
   p.ok = true;
@@ -488,26 +521,26 @@ bool make_input_map(CUtensorMap* map, const void* x, int64_t N, int T_, int H, i
 using Args = x3d::DwTiledArgs;
 
 template <typename T, int MODE, int CC, int TW, int PW, bool XF, bool AUX>
-void launch_one(const TilePlan& p, const CUtensorMap& map, const Args& a, cudaStream_t stream) {
+void launch_one(const TilePlan& p, const CUtensorMap& map, const CUtensorMap& amap, const Args& a, cudaStream_t stream) {
   auto kfn = dw3_tiled_kernel<T, MODE, CC, TW, PW, XF, AUX>;
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
-  x3d::launch(kfn, p.grid, p.threads, p.smem, stream, map, a.w, (T*)a.y, p.g, a.scale, a.shift, a.splits, (const T*)a.aux,
+  x3d::launch(kfn, p.grid, p.threads, p.smem, stream, map, amap, a.w, (T*)a.y, p.g, a.scale, a.shift, a.splits, (const T*)a.aux,
                                              a.stats);
 }
 
 template <typename T, int MODE, int PW>
-int launch_tiled(const TilePlan& p, const CUtensorMap& map, const Args& a, cudaStream_t stream) {
+int launch_tiled(const TilePlan& p, const CUtensorMap& map, const CUtensorMap& amap, const Args& a, cudaStream_t stream) {
   constexpr bool DG = MODE >= 2;
   constexpr int TWa = tw_small<MODE>(), TWb = tw_big<MODE>(), TWc = tw_tiny<MODE>();
   const bool flag = DG ? (a.aux != nullptr) : (a.scale != nullptr);
 #define L2_(CCv, TWv)                                                               \
   do {                                                                              \
-    if (flag) launch_one<T, MODE, CCv, TWv, PW, !DG, DG>(p, map, a, stream);        \
-    else launch_one<T, MODE, CCv, TWv, PW, false, false>(p, map, a, stream);        \
+    if (flag) launch_one<T, MODE, CCv, TWv, PW, !DG, DG>(p, map, amap, a, stream);  \
+    else launch_one<T, MODE, CCv, TWv, PW, false, false>(p, map, amap, a, stream);  \
   } while (0)
 #define L_(CCv)                                    \
   if (p.CC == CCv) {                               \
@@ -530,7 +563,11 @@ int run_tiled(const void* in, int64_t N, int T_, int Hin, int Win, int Ho, int W
   if (!p.ok) return 0;
   CUtensorMap map;
   if (!make_input_map<T>(&map, in, N, T_, Hin, Win, Cp, p.CC, p.IW, p.IH, nan_fill)) return 0;
-  const int rc = launch_tiled<T, MODE, 2>(p, map, a, stream);   // PW = 4 (1 CTA/SM) measured slower
+  CUtensorMap amap = map;                  // only dereferenced by the stride-2 dgrad with the mask epilogue
+  if (MODE == M_DG2 && a.aux != nullptr &&
+      !make_input_map<T>(&amap, a.aux, N, T_, Ho, Wo, Cp, p.CC, p.TW, p.g.TH, false))
+    return 0;
+  const int rc = launch_tiled<T, MODE, 2>(p, map, amap, a, stream);   // PW = 4 (1 CTA/SM) measured slower
   if (rc != 0) return 0;
   *handled = true;
   return 0;
