@@ -184,7 +184,7 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   // aux loads (issued at the start of a plane, needed at its end) were 55 % of its stall samples (ncu).  For that
   // mapping the aux tile of output plane t rides the TMA ring together with input plane t (ring of 4, look-ahead 2)
   // and is read from shared memory one call later.
-  constexpr bool AUXT = AUX && MODE == M_DG2;
+  constexpr bool AUXT = AUX && (MODE == M_DG2 || MODE == M_DG1);
   constexpr int NSTAGE = AUXT ? 4 : 3;
   constexpr int LOOK = AUXT ? 2 : NSTAGE - 1;                    // planes of TMA look-ahead
   constexpr int WR = M::in_ext(PH), WC = M::in_ext(PW);         // per-thread input window
@@ -473,7 +473,7 @@ TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW) {
   const size_t stage_bytes = (plane_bytes + 127) / 128 * 128;
   g.stage_elems = (int)(stage_bytes / esz);
   // stride-2 dgrad with the mask epilogue: 4 ring slots, each with an aux tile [TH][TW][CC] (sized for that case always)
-  const size_t aux_stage_bytes = MODE == M_DG2 ? ((size_t)g.TH * p.TW * p.CC * esz + 127) / 128 * 128 : 0;
+  const size_t aux_stage_bytes = MODE >= M_DG1 ? ((size_t)g.TH * p.TW * p.CC * esz + 127) / 128 * 128 : 0;
   g.aux_stage_elems = (int)(aux_stage_bytes / esz);
   p.smem = (NSTAGE + 1) * stage_bytes + 4 * aux_stage_bytes + (size_t)p.CC * 2 * sizeof(float) +
            (NSTAGE + 1) * sizeof(uint64_t) + 16;
@@ -564,7 +564,7 @@ int run_tiled(const void* in, int64_t N, int T_, int Hin, int Win, int Ho, int W
   CUtensorMap map;
   if (!make_input_map<T>(&map, in, N, T_, Hin, Win, Cp, p.CC, p.IW, p.IH, nan_fill)) return 0;
   CUtensorMap amap = map;                  // only dereferenced by the stride-2 dgrad with the mask epilogue
-  if (MODE == M_DG2 && a.aux != nullptr &&
+  if (MODE >= M_DG1 && a.aux != nullptr &&
       !make_input_map<T>(&amap, a.aux, N, T_, Ho, Wo, Cp, p.CC, p.TW, p.g.TH, false))
     return 0;
   const int rc = launch_tiled<T, MODE, 2>(p, map, amap, a, stream);   // PW = 4 (1 CTA/SM) measured slower
