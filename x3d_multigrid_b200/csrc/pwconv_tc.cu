@@ -102,6 +102,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr, uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+        "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+      : "r"(taddr));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]),
+        "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+      : "r"(taddr + 16));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
 struct TcParams {
   int M, Kp, Np, BN, nk, tmem_cols, ldc;
   int tiles_m;       // number of 128-row tiles (CTAs stride over them)
@@ -359,15 +374,26 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * acc_off + ((uint32_t)(q * 32) << 16);
       __nv_bfloat16* srow = c_s + rloc * p.cpitch;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        if (c0 >= ncols || (p.dbg & 4)) continue;          // (warp-uniform) padding columns of the MMA
+      auto stage16 = [&](int c0, const uint32_t (&r)[16]) {
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
         *reinterpret_cast<uint4*>(srow + c0) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(srow + c0 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+      };
+      // only the chunks that hold real columns are read (BN is the MMA width, ncols <= BN); two loads per wait
+      const int cend = (p.dbg & 4) ? 0 : ncols;
+      int c0 = 0;
+      for (; c0 + 16 < cend; c0 += 32) {
+        uint32_t ra[16], rb[16];
+        tmem_ld16x2(taddr + c0, ra, rb);
+        stage16(c0, ra);
+        stage16(c0 + 16, rb);
+      }
+      if (c0 < cend) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        stage16(c0, r);
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
