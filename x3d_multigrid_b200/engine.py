@@ -103,6 +103,7 @@ class Engine:
         self.arena_f: Optional[Arena] = None
         self.arena_b: Optional[Arena] = None
         self.side = None
+        self.use_side = True        # parallel.DistributedX3D switches it off (see there)
         self.grad_hook: Optional[Callable[[int], None]] = None   # called after each bucket's grads are final
 
     # ------------------------------------------------------------------ parameter tables
@@ -126,7 +127,8 @@ class Engine:
         self.arena_f, self.arena_b = Arena(device), Arena(device)
         # weight-gradient kernels feed nothing downstream: they run on a side stream, concurrently with the
         # dgrad / BN chain of the main stream (fills the SMs that the small late-stage kernels leave idle)
-        self.side = torch.cuda.Stream(device) if (device.type == 'cuda' and not os.environ.get('X3D_NO_SIDE')) else None
+        self.side = torch.cuda.Stream(device) if (device.type == 'cuda' and self.use_side and
+                                                  not os.environ.get('X3D_NO_SIDE')) else None
 
         # ---- flat gradient buffer, bucket order: head+stage4 first ... stem last
         named = dict(m.named_parameters())

@@ -61,6 +61,13 @@ class DistributedX3D(torch.nn.Module):
         if self.world == 1 or getattr(eng, '_ddp_owner', None) is self:
             return
         eng._ddp_owner = self
+        # The bucket allreduces overlap the backward pass here.  With NCCL kernels resident, weight-gradient kernels on
+        # the side stream AND programmatic dependent launch together were measured 2.5x slower (48 vs 18-20 ms/step at
+        # 2 GPUs: early-launched dependents and NCCL compete for the same SM slots), each alone is fine -- this mode
+        # keeps PDL and runs the weight gradients on the main stream.  (Graph mode, bench.py's default, replays
+        # forward+backward without any NCCL kernel in flight and keeps both.)
+        eng.use_side = False
+        eng.side = None
 
         def hook(bucket: int, eng=eng):
             if self._reducer is None or self._reducer.ranges != eng.bucket_ranges:
