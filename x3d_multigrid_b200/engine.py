@@ -367,6 +367,24 @@ class Engine:
         Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
         P_in, P_out = T * H * W, T * Ho * Wo
         af = self.arena_f
+        # downsample branch (x3d.py:165-166): independent of the main chain until the residual add -> side stream
+        ad = bnd = None
+        if blk.downsample is not None:
+            std = self._stats(af, N, Cop) if training else None
+            main = torch.cuda.current_stream(self.device)
+            if self.side is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.side.wait_event(ev)
+                x.record_stream(self.side)
+            with torch.cuda.stream(self.side if self.side is not None else main):
+                ad = self._act(N, T, Ho, Wo, Cop)
+                lib.call('x3d_pwconv_fwd', _ptr(x), self.pk(pre + '.downsample.0.f'), _ptr(ad), N, T, H, W, Cinp, Cop, s,
+                         _ptr(std), dt, self._stream())
+                bnd = self._bn_forward_state(blk.downsample[1], pre + '.downsample.1', std, N, P_out, Co, Cop, training)
+            if self.side is not None:
+                ad.record_stream(main)
+                bnd.scale.record_stream(main)      # scale/shift/mean/rstd share one allocation
         # conv1 + bn1 statistics
         a1 = self._act(N, T, H, W, Cmp)
         st1 = self._stats(af, N, Cmp) if training else None
@@ -397,13 +415,8 @@ class Engine:
                  _ptr(st3), dt, st)
         bn3 = self._bn_forward_state(blk.bn3, pre + '.bn3', st3, N, P_out, Co, Cop, training)
         out = self._act(N, T, Ho, Wo, Cop)
-        ad = bnd = None
         if blk.downsample is not None:
-            ad = self._act(N, T, Ho, Wo, Cop)
-            std = self._stats(af, N, Cop) if training else None
-            lib.call('x3d_pwconv_fwd', _ptr(x), self.pk(pre + '.downsample.0.f'), _ptr(ad), N, T, H, W, Cinp, Cop, s,
-                     _ptr(std), dt, st)
-            bnd = self._bn_forward_state(blk.downsample[1], pre + '.downsample.1', std, N, P_out, Co, Cop, training)
+            self._join_side()                 # the downsample branch (side stream) meets the main chain here
             lib.call('x3d_bn_act_fwd', _ptr(a3), _ptr(bn3.scale), _ptr(bn3.shift), bn3.splits, _ptr(ad),
                      _ptr(bnd.scale), _ptr(bnd.shift), 1, _ptr(out), N, P_out, Cop, dt, st)
         else:
