@@ -437,6 +437,23 @@ class Engine:
         Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
         P_in, P_out = T * H * W, T * Ho * Wo
         ab = self.arena_b
+        # ---- downsample branch: its BN backward only needs dout / out / ad -> side stream, met again at the dgrad
+        dad = ev_dad = None
+        if blk.downsample is not None:
+            main = torch.cuda.current_stream(self.device)
+            if self.side is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.side.wait_event(ev)
+                for t in (dout, out, ad):
+                    t.record_stream(self.side)
+            with torch.cuda.stream(self.side if self.side is not None else main):
+                dad = self._act(N, T, Ho, Wo, Cop)
+                self._bn_backward(ab, pre + '.downsample.1', bnd, dout, out, ad, N, P_out, Co, Cop, dad)
+            if self.side is not None:
+                dad.record_stream(main)
+                ev_dad = torch.cuda.Event()
+                ev_dad.record(self.side)
         # ---- bn3 backward (dpre = dout * [out > 0])
         da3 = self._act(N, T, Ho, Wo, Cop)
         self._bn_backward(ab, pre + '.bn3', bn3, dout, out, a3, N, P_out, Co, Cop, da3)
@@ -493,8 +510,8 @@ class Engine:
                      dt, st)
         # ---- residual branch
         if blk.downsample is not None:
-            dad = self._act(N, T, Ho, Wo, Cop)
-            self._bn_backward(ab, pre + '.downsample.1', bnd, dout, out, ad, N, P_out, Co, Cop, dad)
+            if ev_dad is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev_dad)
             self._wgrad('x3d_pwconv_wgrad', (x, dad), _ptr(x), _ptr(dad), self.g(pre + '.downsample.0.weight'), N, T, H,
                         W, Cin, Cinp, Co, Cop, s, dt)
             if need_dx:
