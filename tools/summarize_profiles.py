@@ -77,7 +77,10 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'launch__grid_size', 'launch__block_size', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
-        'lts__t_bytes.sum', 'smsp__inst_executed.sum']
+        'lts__t_bytes.sum', 'smsp__inst_executed.sum',
+        'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
+        'sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed',
+        'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed']
 for fn in sorted(os.listdir(G)):
     if not (fn.startswith(R) and fn.endswith('.ncu-rep')):
         continue
