@@ -389,17 +389,19 @@ dw3_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   }
 
   if (stats != nullptr) {
+    // block reduction in a fixed order within the CTA (no shared atomics): every thread parks its four partial sums
+    // in its patch's row of a scratch array carved from the (now idle) plane ring, then one thread per (channel,
+    // quantity) adds the rows and issues one fp64 atomic
+    __syncthreads();                       // every plane of the ring has been consumed
+    float* scr = reinterpret_cast<float*>(smem_raw);      // [patches][CC][2] <= 8 * 72 * 2 floats, fits one ring slot
+    float* mine = scr + patch * (CC * 2) + (2 * pair) * 2;
+    *reinterpret_cast<float4*>(mine) = make_float4(ssum.x, ssq.x, ssum.y, ssq.y);
     __syncthreads();
-    for (int i = tid; i < CC * 2; i += nthr) s_stat[i] = 0.f;
-    __syncthreads();
-    atomicAdd(&s_stat[(2 * pair) * 2 + 0], ssum.x);
-    atomicAdd(&s_stat[(2 * pair) * 2 + 1], ssq.x);
-    atomicAdd(&s_stat[(2 * pair + 1) * 2 + 0], ssum.y);
-    atomicAdd(&s_stat[(2 * pair + 1) * 2 + 1], ssq.y);
-    __syncthreads();
+    const int patches = nthr / PAIRS;
     for (int i = tid; i < CC * 2; i += nthr) {
       const int ch = cbase + i / 2;
-      const float v = s_stat[i];
+      float v = 0.f;
+      for (int q = 0; q < patches; ++q) v += scr[q * (CC * 2) + i];
       if (ch < Cp && v != 0.f) atomicAdd(&stats[((int64_t)n * Cp + ch) * 2 + (i & 1)], (double)v);
     }
   }
