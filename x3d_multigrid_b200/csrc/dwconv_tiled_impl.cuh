@@ -625,7 +625,6 @@ dw3_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
-  for (int i = tid; i < 27 * CC; i += nthr) s_red[i] = 0.f;
   __syncthreads();
   x3d::pdl_wait();
   // step s (s = -1 .. T-1) needs x[s] (if s >= 0) and dy[s+1] (if s+1 < T)
@@ -736,18 +735,24 @@ dw3_wgrad_tiled_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_co
   }
 
   // ---- reduction: patches of the CTA -> shared, CTA -> global ------------------------------------
-  if (ch_ok) {
+  // No shared atomics: in three rounds of 9 taps every thread parks its partial sums in its patch's row of a scratch
+  // array carved from the (now idle) ring -- patches x 9 x CC floats = 72 bytes per thread, always smaller than the
+  // ring -- and one thread per (tap, channel) adds the rows in a fixed order and issues ONE fp32 red.
+  float* scr = reinterpret_cast<float*>(smem_raw);
+  const int patches = nthr / PAIRS;
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      atomicAdd(&s_red[k * CC + 2 * pair], gacc[k].x);
-      atomicAdd(&s_red[k * CC + 2 * pair + 1], gacc[k].y);
+  for (int rnd = 0; rnd < 3; ++rnd) {
+    __syncthreads();                       // ring consumed (rnd 0) / previous round summed
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      *reinterpret_cast<float2*>(scr + (patch * 9 + k) * CC + 2 * pair) = gacc[rnd * 9 + k];
+    __syncthreads();
+    for (int i = tid; i < 9 * CC; i += nthr) {
+      const int k = i / CC, cl = i - k * CC, ch = cbase + cl;
+      float v = 0.f;
+      for (int q = 0; q < patches; ++q) v += scr[(q * 9 + k) * CC + cl];
+      if (ch < C && v != 0.f) atomicAdd(&dw[(int64_t)ch * 27 + rnd * 9 + k], v);
     }
-  }
-  __syncthreads();
-  for (int i = tid; i < 27 * CC; i += nthr) {
-    const int k = i / CC, ch = cbase + i % CC;
-    const float v = s_red[i];
-    if (ch < C && v != 0.f) atomicAdd(&dw[(int64_t)ch * 27 + k], v);
   }
 }
 
