@@ -89,3 +89,14 @@ def test_lr_warmup():
     assert opt.param_groups[0]['lr'] == pytest.approx(0.5)
     MG.lr_warmup(1.0, 100, 100, opt)
     assert opt.param_groups[0]['lr'] == pytest.approx(0.5)        # untouched once past the warm-up
+
+
+def test_iteration_plan_equals_sampler_schedule():
+    """the data-free plan (what MultigridTrainer pre-captures graphs for) reproduces the recorded sampler schedule"""
+    g = json.load(open(os.path.join(GOLD, 'sampler_schedule.json')))
+    plan = list(MG.iteration_plan(g['batch_size'], g['schedule'], 16, 224, len(g['rows']), g['long_cycle']))
+    assert [[p['iteration'], p['long_index'], p['batch']] for p in plan] == g['rows']
+    shapes = {(p['long_index'], p['batch'], p['frames'], p['crop']) for p in plan}
+    # 2 + 2 + 3 + 3 shapes of the four long cycles, plus the three of the final phase (long index -1)
+    assert len(shapes) == 13
+    assert (3, 4, 16, 224) in shapes and (0, 64, 4, 111) in shapes and (-1, 16, 16, 112) in shapes
