@@ -21,7 +21,8 @@
 //  * forward epilogue: store + per-(sample,channel) sum / sum-of-squares of the stored values (bn2
 //    statistics and the SE global pool).  dgrad epilogue: ReLU mask of the preceding BN+ReLU recomputed
 //    from the saved conv1 output (aux), store, and the two BN-backward sums (sum d, sum d*aux).
-//    Both: shared atomics -> one fp64 atomic per channel per CTA.
+//    Both: ordered block reduction through a scratch array carved from the idle ring (no shared atomics), then one
+//    fp64 atomic per channel per CTA.
 // Arithmetic intensity of the stride-1 forward in bf16 is 27 FMA / 4 B = 6.75 FMA/B, above the B200
 // balance of ~5.7 FMA/B (37 TFMA/s fp32 vs 6.5 TB/s): those layers are bound by the fp32 FMA pipe, which
 // is why the inner loop is FFMA2 and everything else is kept off that pipe.
@@ -581,7 +582,8 @@ int run_tiled(const void* in, int64_t N, int T_, int Hin, int Win, int Ho, int W
 // tile x[tin] (with halo, BN+ReLU fused on load, NaN -> 0 padding) and the dy tile of plane tin+1; a
 // thread keeps its dy patch of planes tin+1 / tin / tin-1 in registers (they rotate like the forward
 // accumulators) and its 27 x 2 weight-gradient accumulators: every window word feeds up to 27 FFMA2.
-// Reduction: shared atomics across the patches of the CTA, then one fp32 red per (channel, tap) per CTA.
+// Reduction: ordered sum over the patches of the CTA through shared scratch, then one fp32 red per (channel, tap) per CTA
+// (the CTAs are persistent over (sample, tile) units, so this happens once per CTA).
 // =================================================================================================
 template <typename T, int MODE, int CC, int TW, int PW, bool XF>
 __global__ void __launch_bounds__(Cfg<PW>::MAXT, Cfg<PW>::MINB)
