@@ -37,6 +37,29 @@ const char* x3d_last_error(void);
 int x3d_abi_version(void);
 /* number of kernel launches issued through this library since load (all threads) */
 int64_t x3d_launch_count(void);
+/* Which kernel family served a call: every conv entry point below counts the path it took, so that callers
+ * (and the tests) can assert that a hot shape ran the TMA-tiled / tcgen05 kernel and did not silently drop to
+ * the shape-generic fallback.  Counters are process-wide and monotonic. */
+typedef enum {
+  X3D_PATH_DW_FWD_TILED = 0,
+  X3D_PATH_DW_FWD_TEMPORAL = 1,
+  X3D_PATH_DW_FWD_DIRECT = 2,
+  X3D_PATH_DW_DGRAD_TILED = 3,
+  X3D_PATH_DW_DGRAD_TEMPORAL = 4,
+  X3D_PATH_DW_DGRAD_DIRECT = 5,
+  X3D_PATH_DW_WGRAD_TILED = 6,
+  X3D_PATH_DW_WGRAD_TEMPORAL = 7,
+  X3D_PATH_DW_WGRAD_DIRECT = 8,
+  X3D_PATH_PW_FWD_TC = 9,
+  X3D_PATH_PW_FWD_SIMT = 10,
+  X3D_PATH_PW_DGRAD_TC = 11,
+  X3D_PATH_PW_DGRAD_SIMT = 12,
+  X3D_PATH_PW_WGRAD_TC = 13,
+  X3D_PATH_PW_WGRAD_SIMT = 14,
+  X3D_PATH_COUNT = 15
+} x3d_path_t;
+int64_t x3d_path_count(int path);
+const char* x3d_path_name(int path);
 
 /* ---- layout converters (user-facing NCDHW fp32 <-> internal NDHWC) -------------------- */
 int x3d_ncdhw_to_ndhwc(const float* src, void* dst, int64_t N, int64_t C, int64_t Cp, int64_t T,

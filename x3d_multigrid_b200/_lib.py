@@ -98,6 +98,18 @@ class Lib:
     def launch_count(self) -> int:
         return int(self.fn['x3d_launch_count']())
 
+    def path_counts(self) -> Dict[str, int]:
+        """{kernel family: calls served} -- which implementation each conv call took (x3d_path_t); tests assert
+        with this that the hot shapes run the TMA-tiled / tcgen05 kernels, not the shape-generic fallbacks"""
+        n = 0
+        out = {}
+        while True:
+            c = int(self.fn['x3d_path_count'](n))
+            if c < 0:
+                return out
+            out[self.fn['x3d_path_name'](n).decode()] = c
+            n += 1
+
 
 _LIB = None
 

@@ -17,6 +17,10 @@ namespace x3d {
 // ---------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void count_path(int path);      // x3d_path_t
+// Per-DEVICE one-time set-up (cudaFuncSetAttribute is a per-device attribute): returns true the first time the
+// calling site is reached with the current device; `mask` is one static bitmask per call site.
+bool first_use_on_device(unsigned long long* mask);
 
 #define X3D_CHECK_ARG(cond, msg)                    \
   do {                                              \

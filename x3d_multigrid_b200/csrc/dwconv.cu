@@ -148,6 +148,7 @@ extern "C" int x3d_dwconv_fwd(const void* x, const float* w_packed, void* y, int
     bool handled = false;
     int rc = dwconv_temporal(x, w_packed, y, N, T_, H * W, Cp, kt, 0, stats, dt, as_stream(stream), &handled);
     if (handled) {
+      count_path(X3D_PATH_DW_FWD_TEMPORAL);
       if (rc == 0) X3D_LAUNCH_CHECK();
       return rc;
     }
@@ -156,8 +157,12 @@ extern "C" int x3d_dwconv_fwd(const void* x, const float* w_packed, void* y, int
     bool handled = false;
     int rc = dwconv_fwd_tiled(x, w_packed, y, N, T_, H, W, Cp, stride, in_scale, in_shift, splits, relu_in, stats, dt,
                               as_stream(stream), &handled);
-    if (handled) return rc;
+    if (handled) {
+      count_path(X3D_PATH_DW_FWD_TILED);
+      return rc;
+    }
   }
+  count_path(X3D_PATH_DW_FWD_DIRECT);
   X3D_DISPATCH_DTYPE(dt, {
     if (kt == 3) launch_dw_fwd_direct<T, 3, 3, 3>(x, w_packed, y, N, g, in_scale, in_shift, splits, relu_in, stats, as_stream(stream));
     else launch_dw_fwd_direct<T, 5, 1, 1>(x, w_packed, y, N, g, in_scale, in_shift, splits, relu_in, stats, as_stream(stream));
@@ -265,6 +270,7 @@ extern "C" int x3d_dwconv_dgrad(const void* dy, const float* w_packed, void* dx,
     bool handled = false;
     int rc = dwconv_temporal(dy, w_packed, dx, N, T_, H * W, Cp, kt, 1, nullptr, dt, as_stream(stream), &handled);
     if (handled) {
+      count_path(X3D_PATH_DW_DGRAD_TEMPORAL);
       if (rc == 0) X3D_LAUNCH_CHECK();
       return rc;
     }
@@ -273,8 +279,12 @@ extern "C" int x3d_dwconv_dgrad(const void* dy, const float* w_packed, void* dx,
     bool handled = false;
     int rc = dwconv_dgrad_tiled(dy, w_packed, dx, N, T_, H, W, Cp, stride, mask_src, mask_scale, mask_shift, splits,
                                 stats, dt, as_stream(stream), &handled);
-    if (handled) return rc;
+    if (handled) {
+      count_path(X3D_PATH_DW_DGRAD_TILED);
+      return rc;
+    }
   }
+  count_path(X3D_PATH_DW_DGRAD_DIRECT);
 #define L_(KT_, KH_, KW_, MK)                                                                                \
   x3d::launch(dw_dgrad_direct_kernel<T, KT_, KH_, KW_, MK>, grid, rg.threads, smem, as_stream(stream),                   \
       (const T*)dy, w_packed, (T*)dx, g, (const T*)mask_src, mask_scale, mask_shift, splits, stats, P, rg.cv,   \
@@ -386,6 +396,7 @@ extern "C" int x3d_dwconv_wgrad(const void* x, const void* dy, float* dw, int64_
     bool handled = false;
     int rc = dwconv_temporal_wgrad(x, dy, dw, N, T_, H * W, C, Cp, kt, dt, as_stream(stream), &handled);
     if (handled) {
+      count_path(X3D_PATH_DW_WGRAD_TEMPORAL);
       if (rc == 0) X3D_LAUNCH_CHECK();
       return rc;
     }
@@ -394,8 +405,12 @@ extern "C" int x3d_dwconv_wgrad(const void* x, const void* dy, float* dw, int64_
     bool handled = false;
     int rc = dwconv_wgrad_tiled(x, dy, dw, N, T_, H, W, C, Cp, stride, in_scale, in_shift, splits, relu_in, dt,
                                 as_stream(stream), &handled);
-    if (handled) return rc;
+    if (handled) {
+      count_path(X3D_PATH_DW_WGRAD_TILED);
+      return rc;
+    }
   }
+  count_path(X3D_PATH_DW_WGRAD_DIRECT);
 #define L_(KT_, KH_, KW_, XF, RL)                                                                               \
   x3d::launch(dw_wgrad_direct_kernel<T, KT_, KH_, KW_, XF, RL>, grid, rg.threads, smem, as_stream(stream),               \
       (const T*)x, (const T*)dy, dw, g, (int)C, in_scale, in_shift, splits, P, rg.cv, rg.rows, rg.chunk)

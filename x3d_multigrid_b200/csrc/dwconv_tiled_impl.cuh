@@ -526,11 +526,8 @@ using Args = x3d::DwTiledArgs;
 template <typename T, int MODE, int CC, int TW, int PW, bool XF, bool AUX>
 void launch_one(const TilePlan& p, const CUtensorMap& map, const CUtensorMap& amap, const Args& a, cudaStream_t stream) {
   auto kfn = dw3_tiled_kernel<T, MODE, CC, TW, PW, XF, AUX>;
-  static bool attr_done = false;   // per instantiation
-  if (!attr_done) {
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
+  static unsigned long long attr_mask = 0;   // per instantiation, one bit per device
+  if (first_use_on_device(&attr_mask)) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   x3d::launch(kfn, p.grid, p.threads, p.smem, stream, map, amap, a.w, (T*)a.y, p.g, a.scale, a.shift, a.splits, (const T*)a.aux,
                                              a.stats);
 }
@@ -763,11 +760,8 @@ void launch_wgrad_one(const TilePlan& p, const CUtensorMap& xmap, const CUtensor
                       const float* scale, const float* shift, int splits, int C, int dy_stage_elems, size_t smem,
                       cudaStream_t stream) {
   auto kfn = dw3_wgrad_tiled_kernel<T, MODE, CC, TW, 2, XF>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
+  static unsigned long long attr_mask = 0;   // per instantiation, one bit per device
+  if (first_use_on_device(&attr_mask)) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   // persistent grid: as many CTAs per channel chunk as fit the 2 x 148 resident slots, each walking
   // ceil(units / CTAs) (sample, tile) units
   const int nunits = (int)(p.grid.x * p.grid.z);

@@ -23,13 +23,36 @@ bool pdl_enabled() {
   return on;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static std::atomic<int64_t> g_paths[X3D_PATH_COUNT];
+void count_path(int path) {
+  if (path >= 0 && path < X3D_PATH_COUNT) g_paths[path].fetch_add(1, std::memory_order_relaxed);
+}
+bool first_use_on_device(unsigned long long* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  auto* m = reinterpret_cast<std::atomic<unsigned long long>*>(mask);
+  if (m->load(std::memory_order_acquire) & bit) return false;
+  m->fetch_or(bit, std::memory_order_acq_rel);     // a racing thread repeats the (idempotent) set-up: harmless
+  return true;
+}
 }  // namespace x3d
 
 using namespace x3d;
 
 extern "C" const char* x3d_last_error(void) { return x3d::g_err; }
-extern "C" int x3d_abi_version(void) { return 1; }
+extern "C" int x3d_abi_version(void) { return 2; }
 extern "C" int64_t x3d_launch_count(void) { return x3d::g_launches.load(); }
+extern "C" int64_t x3d_path_count(int path) {
+  return (path >= 0 && path < X3D_PATH_COUNT) ? x3d::g_paths[path].load() : -1;
+}
+extern "C" const char* x3d_path_name(int path) {
+  static const char* names[X3D_PATH_COUNT] = {
+      "dw_fwd_tiled",   "dw_fwd_temporal",   "dw_fwd_direct",   "dw_dgrad_tiled", "dw_dgrad_temporal",
+      "dw_dgrad_direct", "dw_wgrad_tiled",   "dw_wgrad_temporal", "dw_wgrad_direct", "pw_fwd_tc",
+      "pw_fwd_simt",    "pw_dgrad_tc",       "pw_dgrad_simt",   "pw_wgrad_tc",    "pw_wgrad_simt"};
+  return (path >= 0 && path < X3D_PATH_COUNT) ? names[path] : "?";
+}
 
 #define ROW_PROLOGUE()                                    \
   constexpr int VEC = Vec<T>::N;                          \

@@ -171,8 +171,12 @@ extern "C" int x3d_pwconv_fwd(const void* x, const void* w, void* y, int64_t N, 
     bool handled = false;
     const int gather[5] = {stride, (int)H, (int)W, map.Ho, map.Wo};
     int rc = pwconv_fwd_tc(x, w, y, M, Kp, Np, P_out, stride > 1 ? gather : nullptr, nullptr, stats, as_stream(stream), &handled);
-    if (handled) return rc;
+    if (handled) {
+      count_path(X3D_PATH_PW_FWD_TC);
+      return rc;
+    }
   }
+  count_path(X3D_PATH_PW_FWD_SIMT);
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(Np, BN));
 #define L_(MA, ST)                                                                                           \
   x3d::launch(pw_gemm_kernel<T, MA, false, ST, false>, grid, 256, 0, as_stream(stream),                               \
@@ -203,8 +207,12 @@ extern "C" int x3d_pwconv_dgrad(const void* dy, const void* wT, void* dx, int64_
     const int scatter[6] = {stride, (int)H, (int)W, map.Ho, map.Wo, accumulate};
     int rc = pwconv_fwd_tc(dy, wT, dx, M, Np, Kp, P_out, nullptr, stride > 1 ? scatter : nullptr, nullptr,
                            as_stream(stream), &handled);
-    if (handled) return rc;
+    if (handled) {
+      count_path(X3D_PATH_PW_DGRAD_TC);
+      return rc;
+    }
   }
+  count_path(X3D_PATH_PW_DGRAD_SIMT);
   // GEMM roles: A = dy [M][Np], B = wT [Kp][Np] (row k holds the Np coefficients), C = dx [.][Kp]
   dim3 grid((unsigned)cdiv(M, BM), (unsigned)cdiv(Kp, BN));
 #define L_(MC, AC)                                                                                           \
@@ -303,8 +311,12 @@ extern "C" int x3d_pwconv_wgrad(const void* x, const void* dy, float* dw, int64_
   if (dt == X3D_BF16 && stride == 1) {
     bool handled = false;
     int rc = pwconv_wgrad_tc(x, dy, dw, M, K, Kp, Nn, Np, as_stream(stream), &handled);
-    if (handled) return rc;
+    if (handled) {
+      count_path(X3D_PATH_PW_WGRAD_TC);
+      return rc;
+    }
   }
+  count_path(X3D_PATH_PW_WGRAD_SIMT);
   const int nt = (int)cdiv(Nn, 64), kt = (int)cdiv(K, 64);
   int64_t splits = cdiv(4 * kNumSMs, (int64_t)nt * kt);
   int64_t max_splits = cdiv(M, 4 * WM);

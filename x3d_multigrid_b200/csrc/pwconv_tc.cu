@@ -770,11 +770,9 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
   if (!make_map_2d(&mapDY, dy, M, Np, WG_ROWS)) return 0;
   if (!make_map_2d(&mapX, x, M, Kp, WG_ROWS)) return 0;
   const size_t smem = 1024 + (size_t)p.stages * (p.a_boxes + p.b_boxes_full) * WG_BOX_BYTES + (2 * WG_MAX_STAGES + 1) * 8 + 16;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_mask = 0;        // per device (the attribute is a per-device property)
+  if (first_use_on_device(&attr_mask))
     cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_done = true;
-  }
   dim3 grid((unsigned)msplit, (unsigned)ntiles, (unsigned)kz);
   static const bool no_cpa = getenv("X3D_TC_NOCPA") != nullptr;
   p.cpa = no_cpa ? 0 : 1;
@@ -849,12 +847,12 @@ int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, 
   if (gx > p.tiles_m) gx = p.tiles_m;
   gx = (p.tiles_m + (p.tiles_m + gx - 1) / gx - 1) / ((p.tiles_m + gx - 1) / gx);   // no empty CTAs
   dim3 grid((unsigned)gx, (unsigned)parts_n);
-  static bool attr_done[2] = {false, false};
+  static unsigned long long attr_mask[2] = {0, 0};   // per device
   if (stats) {
-    if (!attr_done[1]) { cudaFuncSetAttribute(pw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done[1] = true; }
+    if (first_use_on_device(&attr_mask[1])) cudaFuncSetAttribute(pw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     x3d::launch(pw_tc_kernel<true>, grid, NTHREADS, smem, stream, mapA, mapB, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, p, stats);
   } else {
-    if (!attr_done[0]) { cudaFuncSetAttribute(pw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_done[0] = true; }
+    if (first_use_on_device(&attr_mask[0])) cudaFuncSetAttribute(pw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     x3d::launch(pw_tc_kernel<false>, grid, NTHREADS, smem, stream, mapA, mapB, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, p, nullptr);
   }
   *handled = true;

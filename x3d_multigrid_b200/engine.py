@@ -50,8 +50,13 @@ class BNState:
 class Arena:
     """Zero-initialised bump allocator for the small per-step statistic buffers.
 
-    First use of a given step signature measures the need with individual torch.zeros;
-    later steps carve one buffer that is cleared with a single memset."""
+    The first pass of a given step signature measures the need with individual torch.zeros; later passes carve
+    ONE buffer that is cleared with a single memset.  Every ``begin()`` takes a FRESH buffer from the caching
+    allocator instead of recycling the previous one: statistics saved for the backward pass (``st2`` of the SE
+    blocks) stay intact when another forward runs before that backward, and a captured CUDA graph keeps the
+    buffer it was captured with (allocations made during capture live in the graph's private pool), whatever
+    batch sizes are visited afterwards.  ``frame()`` returns the tensors of the current pass; whoever needs them
+    later (the autograd save record) holds on to that."""
 
     def __init__(self, device):
         self.device = device
@@ -61,10 +66,7 @@ class Arena:
         self.keep: List[torch.Tensor] = []
 
     def begin(self):
-        if self.need > 0 and (self.buf is None or self.buf.numel() < self.need):
-            self.buf = torch.empty(self.need, dtype=torch.uint8, device=self.device)
-        if self.buf is not None:
-            self.buf.zero_()
+        self.buf = torch.zeros(self.need, dtype=torch.uint8, device=self.device) if self.need > 0 else None
         self.off = 0
         self.keep = []
 
@@ -79,6 +81,10 @@ class Arena:
             self.off += nbytes
         self.need = max(self.need, self.off)
         return t
+
+    def frame(self):
+        """the tensors backing everything handed out since ``begin()`` (keep a reference to keep them alive)"""
+        return (self.buf, self.keep)
 
 
 class _ParamRef:
@@ -608,18 +614,27 @@ class Engine:
         if x.dtype != torch.float32:
             raise RuntimeError('input clips must be fp32 NCDHW (x3d.py:316)')
         x = x.contiguous()
-        self.prepare(x.device)
-        self.arena_f.begin()
-        self.pack_weights()
-        save = {'blocks': []} if need_grad else None
-        h, geom = self._stem_fwd(x, training, save)
-        for blk in self.model.blocks():
-            h, geom = self.block_fwd(blk, h, geom, training, save['blocks'] if save is not None else None)
-        logits = self._head_fwd(h, geom, training, dropout_mask, save)
+        # kernels launch on the CURRENT device: make it the clip's device (a process may drive several GPUs, e.g.
+        # the nn.DataParallel replicas the reference supports, x3d.py:278-281 / train_..._multigrid.py:175-177)
+        with torch.cuda.device(x.device):
+            self.prepare(x.device)
+            self.arena_f.begin()
+            self.pack_weights()
+            save = {'blocks': []} if need_grad else None
+            h, geom = self._stem_fwd(x, training, save)
+            for blk in self.model.blocks():
+                h, geom = self.block_fwd(blk, h, geom, training, save['blocks'] if save is not None else None)
+            logits = self._head_fwd(h, geom, training, dropout_mask, save)
+            if save is not None:
+                save['arena'] = self.arena_f.frame()      # st2 of the SE blocks is read again by the backward pass
         return logits, save
 
     def backward(self, save, dlogits: torch.Tensor):
         """Accumulates parameter gradients into ``self.gflat`` (zeroed here first)."""
+        with torch.cuda.device(self.device):
+            return self._backward(save, dlogits)
+
+    def _backward(self, save, dlogits: torch.Tensor):
         self.arena_b.begin()
         self.new_grad_buffer()
         d = self._head_bwd(save, dlogits)

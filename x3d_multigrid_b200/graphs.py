@@ -7,8 +7,12 @@ between 2-3 shapes inside a long cycle: keep one ``GraphedTrainStep`` per (B, T,
     step = GraphedTrainStep(model, optimizer, criterion, example_clip, example_labels)
     loss = step(clip, labels)          # copies into the static buffers (async), replays, returns the loss tensor
 
-``optimizer`` should be ``optim.FusedSGD(..., capturable=True)`` so that LR changes reach the graph
-(call ``optimizer.sync_hyper()`` after editing ``param_groups``).
+``optimizer`` should be ``optim.FusedSGD(..., capturable=True)`` so that LR changes reach the graph: the
+hyper-parameters live in a small device tensor that is refreshed (only when ``param_groups`` changed) before
+every replay, so ``lr_sched.step()`` of the reference loop (train_x3d_kinetics_multigrid.py:279) just works.
+
+Building a step runs ``warmup`` real training steps on the example batch; by default the parameters, BN
+buffers and momentum buffers are restored afterwards (``preserve_state=True``).
 
 Data parallel: pass ``reduce_fn`` (e.g. ``lambda: dist.all_reduce(model.engine().gflat)``).  The graph then holds
 forward + backward only; the gradient allreduce (one NCCL call on the flat 15 MB buffer, ~0.1 ms over NVLink) and
@@ -20,9 +24,12 @@ import torch
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, criterion, example_x, example_y, warmup=3, reduce_fn=None,
-                 preserve_state=False):
+                 preserve_state=True):
         self.model, self.opt, self.crit = model, optimizer, criterion
         self.reduce_fn = reduce_fn
+        if warmup < 1:
+            # the first optimizer step initialises the momentum buffers (first_step is baked into a capture)
+            raise ValueError('GraphedTrainStep needs warmup >= 1')
         dev = example_x.device
         # the warm-up steps below are real training steps on the example batch; with preserve_state the parameters,
         # BN buffers and momentum buffers are put back afterwards (in place: the graph keeps their addresses)
@@ -89,14 +96,14 @@ class GraphedTrainStep:
             raise RuntimeError('GraphedTrainStep is bound to one clip shape; keep one instance per multigrid shape')
         self.static_x.copy_(x, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
-        self.graph.replay()
-        if self.reduce_fn is not None:
-            self._finish()
-        return self.static_loss
+        return self.replay()
 
-    def replay(self):
-        """replay on whatever currently sits in static_x / static_y (inputs staged by the caller)"""
+    def replay(self, clone_loss=True):
+        """replay on whatever currently sits in static_x / static_y (inputs staged by the caller).  Returns the loss
+        of THIS step (a copy: the graph overwrites its static loss tensor at the next replay)."""
+        if hasattr(self.opt, 'sync_hyper'):
+            self.opt.sync_hyper()                  # LR / momentum / weight-decay edits since the last step
         self.graph.replay()
         if self.reduce_fn is not None:
             self._finish()
-        return self.static_loss
+        return self.static_loss.clone() if clone_loss else self.static_loss

@@ -78,13 +78,16 @@ class _SubBN(torch.autograd.Function):
             stats = torch.zeros(N, Cp, 2, dtype=torch.float64, device=dev)
             L.call('x3d_bn_bwd_reduce', xn.data_ptr(), None, xn.data_ptr(), stats.data_ptr(), N, P, Cp, F32, st)  # sum x, sum x*x
             sb = mod.split_bn
+            track = sb.track_running_stats and sb.running_mean is not None
             L.call('x3d_bn_finalize', stats.data_ptr(), N, splits, P, C, Cp, gamma.data_ptr(), beta.data_ptr(),
-                   sb.running_mean.data_ptr(), sb.running_var.data_ptr(), sb.num_batches_tracked.data_ptr(),
-                   BN_MOMENTUM, BN_EPS, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), st)
+                   sb.running_mean.data_ptr() if track else None, sb.running_var.data_ptr() if track else None,
+                   sb.num_batches_tracked.data_ptr() if track else None,
+                   float(sb.momentum if sb.momentum is not None else BN_MOMENTUM), float(sb.eps),
+                   scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), st)
         else:
             L.call('x3d_bn_eval_params', gamma.data_ptr(), beta.data_ptr(), mod.bn.running_mean.data_ptr(),
-                   mod.bn.running_var.data_ptr(), C, Cp, BN_EPS, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
-                   rstd.data_ptr(), st)
+                   mod.bn.running_var.data_ptr(), C, Cp, float(mod.bn.eps), scale.data_ptr(), shift.data_ptr(),
+                   mean.data_ptr(), rstd.data_ptr(), st)
         out = torch.empty_like(xn)
         L.call('x3d_bn_act_fwd', xn.data_ptr(), scale.data_ptr(), shift.data_ptr(), splits, None, None, None, 0,
                out.data_ptr(), N, P, Cp, F32, st)
@@ -170,7 +173,7 @@ class _Pointwise(torch.autograd.Function):
     """conv1x1x1 (x3d.py:98-103): y[m][n] = sum_k x[row(m)][k] w[n][k], rows gathered with stride (1,s,s)"""
 
     @staticmethod
-    def forward(ctx, x, w, stride):
+    def forward(ctx, x, w, bias, stride):
         L = _lib.lib()
         N, K, T, H, W = x.shape
         Nn = w.shape[0]
@@ -183,6 +186,14 @@ class _Pointwise(torch.autograd.Function):
         L.call('x3d_pwconv_fwd', xn.data_ptr(), wf.data_ptr(), y.data_ptr(), N, T, H, W, Kp, Np, stride, None, F32, st)
         ctx.save_for_backward(xn, w2)
         ctx.meta = (N, K, Kp, Nn, Np, T, H, W, stride, tuple(w.shape))
+        if bias is not None:        # SE fc1 / fc2 are the only biased 1x1x1 convs (x3d.py:123-124)
+            ones = torch.ones(Np, device=x.device)
+            shift = torch.zeros(Np, device=x.device)
+            shift[:Nn] = bias.detach()
+            yb = torch.empty_like(y)   # y*1 + bias[c] through the BN-apply kernel (scale 1, shift bias)
+            L.call('x3d_bn_act_fwd', y.data_ptr(), ones.data_ptr(), shift.data_ptr(), 1, None, None, None, 0,
+                   yb.data_ptr(), N, T * Ho * Wo, Np, F32, st)
+            y = yb
         return _to_ncdhw(y, Nn)
 
     @staticmethod
@@ -203,12 +214,18 @@ class _Pointwise(torch.autograd.Function):
             dw = torch.zeros(wshape, dtype=torch.float32, device=dy.device)
             L.call('x3d_pwconv_wgrad', xn.data_ptr(), dyn.data_ptr(), dw.data_ptr(), N, T, H, W, K, Kp, Nn, Np, stride,
                    F32, st)
-        return dx, dw, None
+        db = None
+        if ctx.needs_input_grad[2]:
+            Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+            acc = torch.zeros(Np, dtype=torch.float32, device=dy.device)
+            L.call('x3d_colsum', dyn.data_ptr(), N * T * Ho * Wo, Np, acc.data_ptr(), st)
+            db = acc[:Nn].clone()
+        return dx, dw, db, None
 
 
 def pointwise_conv(mod, x):
     x = _check(x, 'pointwise Conv3d.forward')
-    return _Pointwise.apply(x, mod.weight, int(mod.stride[1]))
+    return _Pointwise.apply(x, mod.weight, mod.bias, int(mod.stride[1]))
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -99,28 +99,31 @@ class _BlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, blk, dtype, *params):
         eng = _block_engine(blk, dtype)
-        eng.prepare(x.device)
-        eng.arena_f.begin()
-        eng.pack_weights()
-        N, C, T, H, W = x.shape
-        xin = eng.to_ndhwc(x.contiguous().float())
-        save: List = []
-        out, (_, _, Ho, Wo) = eng.block_fwd(blk, xin, (N, T, H, W), blk.training, save)
-        ctx.eng, ctx.rec = eng, save[0]
-        ctx.in_shape = x.shape
-        return eng.to_ncdhw(out, blk.out_planes)
+        with torch.cuda.device(x.device):
+            eng.prepare(x.device)
+            eng.arena_f.begin()
+            eng.pack_weights()
+            N, C, T, H, W = x.shape
+            xin = eng.to_ndhwc(x.contiguous().float())
+            save: List = []
+            out, (_, _, Ho, Wo) = eng.block_fwd(blk, xin, (N, T, H, W), blk.training, save)
+            ctx.eng, ctx.rec = eng, save[0]
+            ctx.arena = eng.arena_f.frame()               # keeps st2 (read by the backward pass) alive
+            ctx.in_shape = x.shape
+            return eng.to_ncdhw(out, blk.out_planes)
 
     @staticmethod
     def backward(ctx, dy):
         eng = ctx.eng
-        eng.arena_b.begin()
-        eng.new_grad_buffer()
-        d = eng.to_ndhwc(dy.contiguous().float())
-        dx = eng.block_bwd(ctx.rec, d, need_dx=True)
-        eng._join_side()
-        grads = eng.param_grads()
-        out = [g if need else None for g, need in zip(grads, ctx.needs_input_grad[3:])]
-        dxo = eng.to_ncdhw(dx, ctx.in_shape[1]) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(eng.device):
+            eng.arena_b.begin()
+            eng.new_grad_buffer()
+            d = eng.to_ndhwc(dy.contiguous().float())
+            dx = eng.block_bwd(ctx.rec, d, need_dx=True)
+            eng._join_side()
+            grads = eng.param_grads()
+            out = [g if need else None for g, need in zip(grads, ctx.needs_input_grad[3:])]
+            dxo = eng.to_ncdhw(dx, ctx.in_shape[1]) if ctx.needs_input_grad[0] else None
         return (dxo, None, None, *out)
 
 

@@ -6,8 +6,9 @@ buf = d (first step) | momentum*buf + d;  p -= lr*buf.  One param group semantic
 (``param_groups[0]['lr']`` can be edited by LR schedulers / the long-cycle LR law).
 
 ``capturable=True`` reads the hyper-parameters from a small device tensor, so that a captured
-CUDA graph (graphs.GraphedTrainStep) follows later LR changes: call ``sync_hyper()`` (a 16-byte
-H2D copy) before a replay whenever ``param_groups`` changed."""
+CUDA graph (graphs.GraphedTrainStep) follows later LR changes: ``sync_hyper()`` (a 16-byte H2D copy,
+skipped when nothing changed) is called by GraphedTrainStep before every replay, so LR schedulers that
+edit ``param_groups`` directly (MultiStepLR, lr_warmup, the long-cycle law) reach the captured step."""
 from __future__ import annotations
 
 import torch
@@ -22,7 +23,7 @@ class FusedSGD(torch.optim.Optimizer):
         self._tables = {}
         self.grad_scale = 1.0       # e.g. 1/world_size when gradients were summed, not averaged
         self.capturable = capturable
-        self._hyper = {}            # group index -> (device tensor, pinned host tensor)
+        self._hyper = {}            # group index -> device tensor + ring of pinned staging buffers
 
     def _table(self, gi, group):
         ps = [p for p in group['params'] if p.grad is not None]
@@ -53,22 +54,40 @@ class FusedSGD(torch.optim.Optimizer):
         self._tables[gi] = tab
         return tab
 
-    def sync_hyper(self):
-        """push lr / momentum / weight_decay / grad_scale of every group to the device (capturable mode)"""
+    _RING = 4
+
+    def sync_hyper(self, force=False):
+        """push lr / momentum / weight_decay / grad_scale of every group to the device (capturable mode).
+
+        Cheap to call before every replay: nothing is copied when the values are unchanged.  The copy is
+        asynchronous from a small RING of pinned staging buffers, each guarded by an event, so a step that is
+        still queued on the stream never sees the hyper-parameters of a later step."""
         for gi, group in enumerate(self.param_groups):
-            if gi in self._hyper:
-                dev, host = self._hyper[gi]
-                host[0], host[1] = float(group['lr']), float(group['momentum'])
-                host[2], host[3] = float(group['weight_decay']), float(self.grad_scale)
-                dev.copy_(host, non_blocking=True)
+            if gi not in self._hyper:
+                continue
+            st = self._hyper[gi]
+            vals = (float(group['lr']), float(group['momentum']), float(group['weight_decay']), float(self.grad_scale))
+            if vals == st['last'] and not force:
+                continue
+            slot = st['next']
+            st['next'] = (slot + 1) % self._RING
+            host, ev = st['hosts'][slot], st['events'][slot]
+            if ev is not None:
+                ev.synchronize()                      # the copy that last used this slot has executed
+            host[0], host[1], host[2], host[3] = vals
+            st['dev'].copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(st['dev'].device))
+            st['events'][slot] = ev
+            st['last'] = vals
 
     def _hyper_dev(self, gi, group, device):
         if gi not in self._hyper:
-            host = torch.zeros(4, dtype=torch.float32).pin_memory()
-            dev = torch.zeros(4, dtype=torch.float32, device=device)
-            self._hyper[gi] = (dev, host)
+            self._hyper[gi] = {'dev': torch.zeros(4, dtype=torch.float32, device=device),
+                               'hosts': [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(self._RING)],
+                               'events': [None] * self._RING, 'next': 0, 'last': None}
             self.sync_hyper()
-        return self._hyper[gi][0]
+        return self._hyper[gi]['dev']
 
     @torch.no_grad()
     def step(self, closure=None):
