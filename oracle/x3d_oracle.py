@@ -310,7 +310,26 @@ def ce_loss(logits, labels):
     return F.cross_entropy(logits, labels)
 
 
-def loss_and_grads(sd, x, labels, **kw):
+def bce_cls_loss(logits, labels):
+    """Charades classification: nn.BCEWithLogitsLoss on logits.squeeze(2) [B,C] vs multi-hot [B,C],
+    train_x3d_charades.py:122,162,176."""
+    return F.binary_cross_entropy_with_logits(logits.squeeze(2), labels.to(logits.dtype))
+
+
+def bce_loc_loss(logits, labels):
+    """Charades localisation, train_x3d_charades_loc.py:168-189: per-frame logits [B,C,T] are linearly
+    interpolated to the label length TL; loss = (BCE(max_t logits, max_t labels) + BCE(logits, labels)) / 2."""
+    per_frame = F.interpolate(logits, labels.shape[2], mode='linear')
+    lab = labels.to(logits.dtype)
+    cls_loss = F.binary_cross_entropy_with_logits(torch.max(per_frame, dim=2)[0], torch.max(lab, dim=2)[0])
+    loc_loss = F.binary_cross_entropy_with_logits(per_frame, lab)
+    return (cls_loss + loc_loss) / 2
+
+
+LOSSES = {'ce': ce_loss, 'bce': bce_cls_loss, 'bce_loc': bce_loc_loss}
+
+
+def loss_and_grads(sd, x, labels, loss='ce', **kw):
     """One fwd+bwd: returns (logits, loss, {param key: grad}, new running stats)."""
     params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()
               if v.is_floating_point() and 'running_' not in k}
@@ -318,7 +337,7 @@ def loss_and_grads(sd, x, labels, **kw):
     full.update(params)
     new_stats: dict = {}
     logits = forward(full, x, new_stats=new_stats, **kw)
-    loss = ce_loss(logits, labels)
+    loss = LOSSES[loss](logits, labels)
     loss.backward()
     grads = {k: p.grad for k, p in params.items() if p.grad is not None}
     return logits.detach(), loss.detach(), grads, new_stats

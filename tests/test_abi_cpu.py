@@ -20,8 +20,11 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(cdll, n), f'{n} declared in include/x3d_b200.h but not exported'
     L = _lib.lib()
-    assert L.fn['x3d_abi_version']() == 1
+    assert L.fn['x3d_abi_version']() == 2
     assert L.launch_count() == 0            # nothing may launch without a GPU
+    paths = L.path_counts()                 # kernel-family counters (x3d_path_t)
+    assert len(paths) == 15 and 'pw_fwd_tc' in paths and 'dw_wgrad_tiled' in paths
+    assert all(v == 0 for v in paths.values())
 
 
 def test_struct_layouts_match_header():

@@ -13,7 +13,7 @@ import torch
 
 from conftest import GOLDEN
 from oracle import x3d_oracle as O
-from oracle.make_golden import CASES
+from oracle.make_golden import CASES, case_clip
 
 REF = '/root/reference'
 
@@ -27,16 +27,19 @@ def _rel(a, b):
 def _run_oracle(case, conv_impl):
     c = CASES[case]
     sd = O.make_state_dict(c['version'], c['n_classes'], c['splits'])
-    x = O.det_clip(c['shape'])
+    x = case_clip(c['shape'])
     gold = np.load(os.path.join(GOLDEN, case + '.npz'))
     labels = torch.from_numpy(gold['labels'])
-    logits, loss, grads, stats = O.loss_and_grads(sd, x, labels, version=c['version'], splits=c['splits'],
-                                                  training=True, task=c['task'], conv_impl=conv_impl)
+    logits, loss, grads, stats = O.loss_and_grads(sd, x, labels, loss=c.get('loss', 'ce'), version=c['version'],
+                                                  splits=c['splits'], training=True, task=c['task'],
+                                                  conv_impl=conv_impl)
     return gold, sd, x, logits, loss, grads, stats
 
 
 @pytest.mark.parametrize('case,conv_impl', [('s_small_split2', 'explicit'), ('s_small_split2', 'aten'),
-                                            ('m_odd_loc', 'explicit'), ('m_odd_loc', 'aten')])
+                                            ('m_odd_loc', 'explicit'), ('m_odd_loc', 'aten'),
+                                            ('m_charades_cls', 'aten'), ('m_charades_loc', 'aten'),
+                                            ('xl_small', 'aten'), ('m_mg_111', 'aten')])
 def test_oracle_matches_reference_golden(case, conv_impl):
     gold, sd, x, logits, loss, grads, stats = _run_oracle(case, conv_impl)
     assert _rel(logits.numpy(), gold['logits']) < 1e-10
@@ -77,10 +80,47 @@ def test_oracle_config1_logits():
     c = CASES['s_config1']
     gold = np.load(os.path.join(GOLDEN, 's_config1.npz'))
     sd = O.make_state_dict(c['version'], c['n_classes'], c['splits'])
-    x = O.det_clip(c['shape'])
+    x = case_clip(c['shape'])
     with torch.no_grad():
         logits = O.forward(sd, x, version='S', splits=1, training=True, conv_impl='aten')
     assert _rel(logits.numpy(), gold['logits']) < 1e-10
+
+
+def test_by_split_equivalence():
+    """oracle/make_golden.py produces the BASELINE config-2 golden (batch 16, 2 BN splits) split by split: the
+    network on x with s splits equals s independent runs on x[b::s] with one split (x3d.py:47-52).  Checked
+    here on a small case: logits interleave, loss / gradients average, running statistics concatenate."""
+    sd2 = O.make_state_dict('S', 13, 2)
+    sd1 = O.make_state_dict('S', 13, 1)
+    x = case_clip((4, 3, 4, 24, 28))
+    labels = torch.tensor([[1], [5], [9], [12]])
+    lg, ls, g, st = O.loss_and_grads(sd2, x, labels, version='S', splits=2, training=True, conv_impl='aten')
+    acc, loss = {}, 0.0
+    for b in range(2):
+        rows = torch.arange(b, 4, 2)
+        lgb, lsb, gb, stb = O.loss_and_grads(sd1, x[rows], labels[rows], version='S', splits=1, training=True,
+                                             conv_impl='aten')
+        assert _rel(lgb.numpy(), lg[rows].numpy()) < 1e-12
+        loss += lsb.item() / 2
+        for k, v in gb.items():
+            acc[k] = v / 2 if k not in acc else acc[k] + v / 2
+        for k, v in stb.items():
+            C = v.numel()
+            assert _rel(v.numpy(), st[k][b * C:(b + 1) * C].numpy()) < 1e-12, k
+    assert abs(loss - ls.item()) < 1e-12
+    for k, v in g.items():
+        assert _rel(acc[k].numpy(), v.numpy()) < 1e-9, k
+
+
+@pytest.mark.slow
+def test_golden_config2_summary_is_consistent():
+    """the committed BASELINE config-2 fixtures exist and carry what the GPU tests read"""
+    for case in ('m_config2', 'm_config2_b4'):
+        gold = np.load(os.path.join(GOLDEN, case + '.npz'))
+        B = CASES[case]['shape'][0]
+        assert gold['logits'].shape == (B, 400, 1) and gold['eval_logits'].shape == (B, 400, 1)
+        assert abs(float(gold['loss']) - np.log(400)) < 0.2          # near-uniform logits at init
+        assert gold['stat/bn1.split_bn.running_mean'].shape == (2 * 24,)
 
 
 def test_manifest_matches_reference():
@@ -114,6 +154,6 @@ def test_oracle_matches_live_reference_block():
     sd = O.det_fill_state_dict(m.state_dict())
     m.load_state_dict(sd)
     m.train()
-    x = O.det_clip((4, 3, 3, 20, 24))
+    x = case_clip((4, 3, 3, 20, 24))
     got = O.forward(sd, x, version='S', splits=2, training=True)
     assert _rel(got.detach().numpy(), m(x).detach().numpy()) < 1e-10
