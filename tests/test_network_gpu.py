@@ -12,13 +12,16 @@ import numpy as np
 import pytest
 import torch
 
+import json
+
 from conftest import GOLDEN
 from oracle import x3d_oracle as O
-from oracle.make_golden import CASES
+from oracle.make_golden import CASES, case_clip
 
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+BF16_BLOCK_MARGIN = 1.0     # x the reference-autocast error of the same tensor (see test_bottleneck_standalone)
 
 
 def rel(a, b):
@@ -66,34 +69,75 @@ def test_bottleneck_standalone(cfg, dtype):
     tol = TOL[dtype]
     assert y.shape == yref.shape
     assert rel(y, yref.detach()) < tol
-    assert rel(x.grad, x64.grad) < (3 * tol if dtype == torch.float32 else 0.1)
-    # Parameter gradients upstream of bn2 pass through the ill-conditioned dw-conv -> train-mode-BN
-    # pair: storage rounding of the BN-backward output is amplified ~40x, so in bf16
-    # they are graded loosely here (and at the north_star tolerance in fp32).
-    gtol = 5 * tol if dtype == torch.float32 else 0.3
-    errs = {}
+    errs = {'dx': rel(x.grad, x64.grad)}
     for k, p in blk.named_parameters():
-        g = leaves['blk.' + k].grad
-        errs[k] = rel(p.grad, g)
-    print('block grad errors', dtype, {k: f'{v:.2e}' for k, v in errs.items()})
-    for k, v in errs.items():
-        assert v < gtol, (k, v)
+        errs[k] = rel(p.grad, leaves['blk.' + k].grad)
+    print('block grad errors', dtype, cfg, {k: f'{v:.2e}' for k, v in errs.items()})
+    if dtype == torch.float32:
+        assert errs['dx'] < 3 * tol
+        for k, v in errs.items():
+            assert v < 5 * tol, (k, v)
+    else:
+        # bf16: gradients pass through the ill-conditioned dw-conv -> train-mode-BN pair (rounding of
+        # the BN-backward output is amplified ~40x), and NO bf16 execution holds 2e-2 here: the unmodified reference
+        # Bottleneck under torch.autocast(bf16) is 3e-2 ... 1.6e-1 away from its own fp64 run on these very inputs
+        # (tools/bf16_block_noise.py -> tests/golden/bf16_block_noise.json, produced in the build container).
+        # Bound per tensor: the north_star's 2e-2, or the reference's own bf16 error where that is larger.
+        with open(os.path.join(GOLDEN, 'bf16_block_noise.json')) as f:
+            noise = json.load(f)['cases'][f'cfg{cfg} x{tuple(x.shape)}']
+        for k, v in errs.items():
+            assert v <= max(2e-2, BF16_BLOCK_MARGIN * noise[k]), (k, v, noise[k])
     for k, v in new_stats.items():
         got = dict(blk.named_buffers())[k[len('blk.'):]]
         assert rel(got, v) < tol, k
 
 
 def _run_net(case, dtype):
+    """one training forward+backward of golden case `case` (clip, targets and loss as oracle/make_golden.py)"""
     c = CASES[case]
     m, sd = build(c['version'], c['n_classes'], c['splits'], c['task'], dtype)
     gold = np.load(os.path.join(GOLDEN, case + '.npz'))
-    x = O.det_clip(c['shape'], dtype=torch.float32).cuda()
+    x = case_clip(c['shape']).float().cuda()          # fp32-representable: exactly the clip the reference ran on
     labels = torch.from_numpy(gold['labels']).cuda()
     m.train()
     logits = m(x)
-    loss = torch.nn.functional.cross_entropy(logits, labels)
+    loss = O.LOSSES[c.get('loss', 'ce')](logits, labels)
     loss.backward()
     return m, sd, gold, x, labels, logits, loss
+
+
+def _check_golden_grads(m, gold, floor, factor_of=None, factor=3.0):
+    """parameter gradients against what the REFERENCE produced (golden): first 16 entries + norm of every
+    parameter, and the full tensors stored under gfull/.  Bound: `floor`, or `factor` x the reference-fp32 error
+    of the same parameter (`factor_of`, SURVEY 4.1 protocol item 3) where given."""
+    worst = []
+    for k, p in m.named_parameters():
+        bound = floor if factor_of is None else max(floor, factor * factor_of[k])
+        e = rel(p.grad.reshape(-1)[:16], gold['ghead/' + k])
+        en = abs(float(p.grad.double().norm()) - float(gold['gnorm/' + k])) / (float(gold['gnorm/' + k]) + 1e-300)
+        worst.append((max(e, en), k))
+        assert e <= bound and en <= bound, (k, e, en, bound)
+        if 'gfull/' + k in gold.files:
+            ef = rel(p.grad, gold['gfull/' + k])
+            assert ef <= bound, (k, ef, bound)
+    worst.sort(reverse=True)
+    return worst[:4]
+
+
+def _paths():
+    from x3d_multigrid_b200 import _lib
+    return _lib.lib().path_counts()
+
+
+def _assert_fast_paths(before, allow_simt_fwd=0, allow_simt_wgrad=0):
+    """every depthwise call ran the TMA-tiled (or streaming temporal) kernel and every pointwise call the tcgen05
+    kernel, except the named number of strided / wide-K layers that are still SIMT"""
+    d = {k: v - before[k] for k, v in _paths().items()}
+    assert d['dw_fwd_direct'] == d['dw_dgrad_direct'] == d['dw_wgrad_direct'] == 0, d
+    assert d['dw_fwd_tiled'] >= 26 and d['dw_dgrad_tiled'] >= 26 and d['dw_wgrad_tiled'] >= 26, d
+    assert d['pw_fwd_simt'] <= allow_simt_fwd and d['pw_dgrad_simt'] == 0 and d['pw_wgrad_simt'] <= allow_simt_wgrad, d
+    assert d['pw_fwd_tc'] >= 50 and d['pw_dgrad_tc'] >= 50 and d['pw_wgrad_tc'] >= 50, d
+    return d
 
 
 @pytest.mark.parametrize('case', ['s_small_split2', 'm_odd_loc'])
@@ -117,16 +161,14 @@ def test_network_fp32_matches_reference_golden(case):
     # re-checked here against the golden heads / norms the reference produced)
     _, _, g64, _ = O.loss_and_grads(sd, x.double().cpu(), labels.cpu(), version=c['version'], splits=c['splits'],
                                     training=True, task=c['task'], conv_impl='aten')
-    report = []
+    report, eref = [], {}
     for k, p in m.named_parameters():
-        if k.split('.')[0] in ('fc2', 'fc1', 'bn5'):
-            # head gradients do not pass through a BN backward: well conditioned, so the fp64 oracle run on
-            # this box must reproduce the reference's golden values (deeper ones differ by up to 1e-2 between
-            # two fp64 executions on different CPUs -- they are graded against the local anchor only)
-            assert rel(g64[k].reshape(-1)[:16], gold['ghead/' + k]) < 1e-4, k
-            assert abs(float(g64[k].norm()) - float(gold['gnorm/' + k])) <= 1e-4 * float(gold['gnorm/' + k]) + 1e-12, k
+        # the fp64 oracle run on this box reproduces what the reference produced (same fp32-representable clip)
+        assert rel(g64[k].reshape(-1)[:16], gold['ghead/' + k]) < 1e-5, k
+        assert abs(float(g64[k].norm()) - float(gold['gnorm/' + k])) <= 1e-5 * float(gold['gnorm/' + k]) + 1e-12, k
         err_new = rel(p.grad, g64[k])
         err_ref = rel(g32[k], g64[k])
+        eref[k] = err_ref
         report.append((err_new, err_ref, k))
         # factor 3: err_ref is ONE sample of the fp32 rounding noise of the reference; the kernels' own run-to-run
         # noise (fp32 atomics order in the statistics / weight-gradient reductions) reaches 2.2x of it about once in
@@ -135,6 +177,8 @@ def test_network_fp32_matches_reference_golden(case):
     report.sort(reverse=True)
     print(f'fp32 [{case}] worst param-grad errors vs fp64 (ours, reference-fp32): '
           + ', '.join(f'{k}: {a:.1e}/{b:.1e}' for a, b, k in report[:4]))
+    # and directly against the reference-produced golden gradients (heads, norms, the full gfull/* tensors)
+    _check_golden_grads(m, gold, 1e-4, factor_of=eref)
     # eval path: aggregate_sub_bn_stats + eval forward (x3d.py:306-313, :54)
     m.aggregate_sub_bn_stats()
     m.eval()
@@ -303,3 +347,243 @@ def test_multigrid_trainer_graphs_match_eager_and_oracle_schedule():
     assert torch.allclose(sg['bn1.split_bn.running_mean'], se['bn1.split_bn.running_mean'], atol=2e-5, rtol=5e-2)
     # the BN split count follows the long cycle (base 1 x LONG_CYCLE[2] = 2 at the end)
     assert mg.bn1.num_splits == 2 and mg.bn1.split_bn.num_features == 2 * 24
+
+
+# =========================================================================================================
+# BASELINE configs at production size against goldens produced by the reference itself
+# =========================================================================================================
+def _stat_errors(m, gold):
+    bufs = dict(m.named_buffers())
+    worst_var, worst_mean_sd = 0.0, 0.0
+    for k in gold.files:
+        if not k.startswith('stat/'):
+            continue
+        mine, ref = bufs[k[5:]].double().cpu(), torch.as_tensor(gold[k]).double()
+        if k.endswith('running_var'):
+            worst_var = max(worst_var, rel(mine, ref))
+        else:   # running means of deep layers are ~0: grade them in units of the matching standard deviation
+            std = torch.as_tensor(gold[k.replace('running_mean', 'running_var')]).double().sqrt()
+            worst_mean_sd = max(worst_mean_sd, float((mine - ref).norm() / std.norm()))
+    return worst_var, worst_mean_sd
+
+
+def test_config2_bf16_matches_reference_golden():
+    """BASELINE config 2 -- the shape bench.py times: X3D-M, batch 16, 16x224x224, bf16 storage, 2 BN splits --
+    against the golden the unmodified reference produced in fp64 (oracle/make_golden.py, case m_config2)."""
+    before = _paths()
+    m, sd, gold, x, labels, logits, loss = _run_net('m_config2', torch.bfloat16)
+    d = _assert_fast_paths(before, allow_simt_fwd=1, allow_simt_wgrad=4)
+    e = rel(logits, gold['logits'])
+    wv, wm = _stat_errors(m, gold)
+    top1 = float((logits.argmax(1).cpu() == torch.from_numpy(gold['logits']).argmax(1)).float().mean())
+    print(f'config2 bf16: logits rel {e:.3e}, loss {loss.item():.5f} vs {float(gold["loss"]):.5f}, running var rel '
+          f'{wv:.2e}, running mean err/std {wm:.2e}, top-1 agreement {top1:.2f} (|logit| < 0.65 at init), paths {d}')
+    assert e < 2e-2
+    assert abs(loss.item() - float(gold['loss'])) < 2e-2 * float(gold['loss'])
+    assert wv < 2e-2 and wm < 2e-2
+    # head gradients (no BN backward between them and the loss) at the bf16 tolerance
+    for k in ('fc2.bias', 'fc2.weight', 'fc1.weight'):
+        p = dict(m.named_parameters())[k]
+        assert rel(p.grad.reshape(-1)[:16], gold['ghead/' + k]) < 2e-2, k
+    for p in m.parameters():
+        assert torch.isfinite(p.grad).all()
+    # eval path on the aggregated statistics
+    m.aggregate_sub_bn_stats()
+    m.eval()
+    with torch.no_grad():
+        ev = m(x)
+    ee = rel(ev, gold['eval_logits'])
+    print(f'config2 bf16: eval logits rel {ee:.3e}')
+    assert ee < 2e-2
+
+
+def test_config2_batch4_fp32_matches_reference_golden():
+    """same clip size, batch 4, fp32 storage: production-size tilings of every kernel at the fp32 tolerance"""
+    m, sd, gold, x, labels, logits, loss = _run_net('m_config2_b4', torch.float32)
+    assert rel(logits, gold['logits']) < 1e-4
+    assert abs(loss.item() - float(gold['loss'])) < 1e-4
+    bufs = dict(m.named_buffers())
+    for k in gold.files:
+        if k.startswith('stat/'):
+            assert rel(bufs[k[5:]], gold[k]) < 1e-4, k
+    # head gradients are well conditioned; the deep ones carry the train-mode-BN amplification (SURVEY 4.1): report
+    for k in ('fc2.bias', 'fc2.weight', 'fc1.weight', 'bn5.weight', 'bn5.bias'):
+        p = dict(m.named_parameters())[k]
+        assert rel(p.grad.reshape(-1)[:16], gold['ghead/' + k]) < 1e-4, k
+    errs = sorted(((rel(p.grad.reshape(-1)[:16], gold['ghead/' + k]), k) for k, p in m.named_parameters()), reverse=True)
+    print('config2 b4 fp32: worst ghead errors ' + ', '.join(f'{k} {e:.1e}' for e, k in errs[:4]))
+    assert errs[0][0] < 5e-2          # reference fp32 vs fp64 is ~1e-2 on these (SURVEY 4.1)
+    m.aggregate_sub_bn_stats()
+    m.eval()
+    with torch.no_grad():
+        assert rel(m(x), gold['eval_logits']) < 1e-4
+
+
+@pytest.mark.parametrize('case', ['m_mg_111', 'xl_small', 'm_charades_cls', 'm_charades_loc'])
+def test_more_configs_fp32_and_bf16(case):
+    """BASELINE config 3 (a multigrid shape: B=8, T=4, H=111, BN splits 4), config 4 (X3D-XL widths) and config 5
+    (Charades heads: 157-way BCE; 'loc' head + F.interpolate + cls/loc BCE) against reference goldens."""
+    c = CASES[case]
+    before = _paths()
+    m, sd, gold, x, labels, logits, loss = _run_net(case, torch.float32)
+    assert logits.shape == gold['logits'].shape
+    assert rel(logits, gold['logits']) < 1e-4
+    assert abs(loss.item() - float(gold['loss'])) < 1e-4
+    bufs = dict(m.named_buffers())
+    for k in gold.files:
+        if k.startswith('stat/'):
+            assert rel(bufs[k[5:]], gold[k]) < 1e-4, k
+    heads = ('fc2.bias', 'fc2.weight', 'fc1.weight')
+    for k in heads:
+        assert rel(dict(m.named_parameters())[k].grad.reshape(-1)[:16], gold['ghead/' + k]) < 1e-4, k
+    errs = sorted(((rel(p.grad.reshape(-1)[:16], gold['ghead/' + k]), k) for k, p in m.named_parameters()), reverse=True)
+    print(f'[{case}] fp32 worst ghead errors ' + ', '.join(f'{k} {e:.1e}' for e, k in errs[:3]))
+    m.aggregate_sub_bn_stats()
+    m.eval()
+    with torch.no_grad():
+        assert rel(m(x), gold['eval_logits']) < 1e-4
+    # bf16 storage: loss at the north_star tolerance, logits reported (near-uniform at init, tiny clips)
+    before = _paths()
+    m, sd, gold, x, labels, logits, loss = _run_net(case, torch.bfloat16)
+    d = {k: v - before[k] for k, v in _paths().items()}
+    print(f'[{case}] bf16 logits rel {rel(logits, gold["logits"]):.3e}, loss {loss.item():.5f} vs '
+          f'{float(gold["loss"]):.5f}; paths {d}')
+    assert abs(loss.item() - float(gold['loss'])) < 2e-2 * float(gold['loss'])
+    assert d['dw_fwd_direct'] == 0 and d['dw_dgrad_direct'] == 0 and d['dw_wgrad_direct'] == 0, d
+    for p in m.parameters():
+        assert torch.isfinite(p.grad).all()
+
+
+def test_top1_identity_on_peaked_logits():
+    """argmax identity needs peaked logits (at init they are ~uniform, |logit| < 0.7).  A seeded
+    8-step fit of X3D-S on 4 fixed clips (CUDA path, fp32) makes them peaked (|logit| ~ 10); the fitted weights are
+    then run by the CUDA path (fp32 and bf16 storage) and by the fp64 oracle on the same clips in train-mode BN
+    (batch statistics, what the training loop evaluates): identical top-1, logits at the stated tolerance."""
+    from x3d_multigrid_b200.optim import FusedSGD
+    m, sd = build('S', 11, 1, 'class', torch.float32)
+    xs = case_clip((8, 3, 4, 48, 48)).float().cuda()
+    ys = torch.tensor([[1], [4], [7], [10], [2], [5], [8], [0]]).cuda()
+    opt = FusedSGD(m.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-5)
+    m.train()
+    for _ in range(8):
+        opt.zero_grad(set_to_none=True)
+        torch.nn.functional.cross_entropy(m(xs[:4]), ys[:4]).backward()
+        opt.step()
+    fitted = {k: v.detach().double().cpu() if v.is_floating_point() else v.cpu() for k, v in m.state_dict().items()}
+    for name, clips in (('fitted clips', xs[:4]), ('all clips', xs)):
+        with torch.no_grad():
+            want = O.forward(fitted, clips.double().cpu(), version='S', splits=1, training=True, conv_impl='aten')
+            got32 = m.set_compute_dtype(torch.float32)(clips)
+            got16 = m.set_compute_dtype(torch.bfloat16)(clips)
+        top2 = want.squeeze(2).topk(2, 1).values
+        margin = float((top2[:, 0] - top2[:, 1]).min())
+        spread = float(want.abs().max())
+        e32, e16 = rel(got32, want), rel(got16, want)
+        print(f'peaked logits [{name}]: absmax {spread:.2f}, smallest top-1 margin {margin:.3f}, fp32 rel {e32:.2e}, '
+              f'bf16 rel {e16:.2e}')
+        assert spread > 3.0                                        # the fit made them peaked
+        assert e32 < 1e-4 and e16 < 2e-2
+        assert torch.equal(got32.argmax(1).cpu(), want.argmax(1))
+        # bf16: identical top-1 wherever the oracle's own margin exceeds the bf16 logit error
+        err16 = float((got16.double().cpu() - want).abs().max())
+        sure = (top2[:, 0] - top2[:, 1]) > 2 * err16
+        assert bool(sure[:4].all()) or name != 'fitted clips'
+        assert torch.equal(got16.argmax(1).cpu()[sure], want.argmax(1)[sure])
+    assert torch.equal(got32[:4].argmax(1).flatten().cpu(), ys[:4].flatten().cpu())    # and it learned the 4 clips
+
+
+# =========================================================================================================
+# engine state: arenas, graphs, hyper-parameters, devices
+# =========================================================================================================
+def test_two_forwards_before_backward():
+    """a second forward before the first backward must not disturb the first one's saved statistics
+    (fwd(x1), fwd(x2), (l1+l2).backward() == separate backward passes)"""
+    m, sd = build('S', 5, 2, 'class', torch.float32)
+    m.eval()            # running-stat BN: well conditioned, so the comparison can be tight
+    x1 = case_clip((2, 3, 4, 32, 32)).float().cuda()
+    x2 = O.det_clip((2, 3, 4, 32, 32), 'clip2', torch.float32).cuda()
+    y = torch.tensor([[1], [3]]).cuda()
+    ce = torch.nn.functional.cross_entropy
+    ce(m(x1), y).backward()
+    ce(m(x2), y).backward()
+    want = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    l1 = ce(m(x1), y)
+    l2 = ce(m(x2), y)
+    (l1 + l2).backward()
+    for k, p in m.named_parameters():
+        assert rel(p.grad, want[k]) < 1e-5, k
+    # train mode (split statistics saved by the SE blocks come from the arena): forward of x2 must not corrupt x1's
+    m.train()
+    m.zero_grad(set_to_none=True)
+    ce(m(x1), y).backward()
+    ref = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    l1 = ce(m(x1), y)
+    with torch.no_grad():
+        m(x2)
+    l1.backward()
+    for k in ('layer1.0.fc1.weight', 'layer1.0.bn2.weight', 'layer3.0.fc2.bias', 'fc2.bias'):
+        assert rel(dict(m.named_parameters())[k].grad, ref[k]) < 1e-3, k
+
+
+def test_graphs_survive_growing_batches_and_follow_lr_schedulers():
+    """(a) graphs captured for a small batch stay valid after larger batches were captured (each capture keeps
+    its own statistics arena); (b) a MultiStepLR milestone edits param_groups directly: graph mode must follow
+    it like eager mode (train_x3d_kinetics_multigrid.py:184,279)."""
+    from x3d_multigrid_b200.graphs import GraphedTrainStep
+    from x3d_multigrid_b200.optim import FusedSGD
+
+    def run(use_graph):
+        m, _ = build('S', 7, 1)
+        m.train()
+        opt = FusedSGD(m.parameters(), lr=1e-3, momentum=0.9, weight_decay=5e-5, capturable=True)
+        sched = torch.optim.lr_scheduler.MultiStepLR(opt, [2], gamma=0.1)
+        crit = torch.nn.CrossEntropyLoss()
+        batches = []
+        for B in (1, 2, 4):                                   # ascending batch sizes
+            batches.append((O.det_clip((B, 3, 4, 32, 32), f'gx{B}', torch.float32).cuda(),
+                            (torch.arange(B) % 7).view(B, 1).cuda()))
+        steps = {}
+        losses = []
+        for it in range(6):
+            x, y = batches[it % 3] if it < 3 else batches[0]   # ... then back to the FIRST (smallest) shape
+            if use_graph:
+                key = tuple(x.shape)
+                if key not in steps:
+                    steps[key] = GraphedTrainStep(m, opt, crit, x, y)
+                losses.append(float(steps[key](x, y)))
+            else:
+                opt.zero_grad(set_to_none=True)
+                loss = crit(m(x), y)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss))
+            sched.step()
+        torch.cuda.synchronize()
+        return m, losses, opt
+
+    mg, lg, og = run(True)
+    me, le, oe = run(False)
+    assert og.param_groups[0]['lr'] == pytest.approx(1e-4) == oe.param_groups[0]['lr']
+    assert np.allclose(lg, le, rtol=2e-2), (lg, le)
+    d_g = mg.fc2.bias.detach().double().cpu()
+    d_e = me.fc2.bias.detach().double().cpu()
+    b0 = O.make_state_dict('S', 7, 1)['fc2.bias'].double()
+    # a missed LR decay would make the last 3 updates 10x larger: the total update would differ by ~2x
+    assert rel(d_g - b0, d_e - b0) < 0.15, rel(d_g - b0, d_e - b0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs in one process')
+def test_second_device_in_one_process():
+    """per-device kernel attributes / caches: the same process drives cuda:0 then cuda:1 (nn.DataParallel case)"""
+    x = case_clip((2, 3, 4, 64, 64)).float()
+    outs = []
+    for dev in (0, 1):
+        m, _ = build('S', 5, 1, 'class', torch.bfloat16)
+        m = m.to(f'cuda:{dev}').train()
+        logits = m(x.to(f'cuda:{dev}'))
+        torch.nn.functional.cross_entropy(logits, torch.tensor([[1], [3]], device=f'cuda:{dev}')).backward()
+        torch.cuda.synchronize(dev)
+        outs.append(logits.detach().float().cpu())
+    assert rel(outs[1], outs[0]) < 2e-2
