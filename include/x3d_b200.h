@@ -142,6 +142,12 @@ int x3d_bn_act_fwd(const void* a, const float* scale, const float* shift, int sp
 /* BN backward, pass 1: dpre = dout * (mask_out > 0 if mask_out) ; stats += {sum dpre, sum dpre*a} */
 int x3d_bn_bwd_reduce(const void* dout, const void* mask_out, const void* a, double* stats,
                       int64_t N, int64_t P, int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream);
+/* same, and dpre is also written out: the identity-residual block keeps it as the start value of its input
+ * gradient (dx = dpre + conv1 dgrad, x3d.py:168-169), so neither the apply pass below nor a separate
+ * "dx += dout*(out>0)" pass reads dout / the mask source again */
+int x3d_bn_bwd_reduce_store(const void* dout, const void* mask_out, const void* a, double* stats,
+                            void* dpre_out, int64_t N, int64_t P, int64_t Cp, x3d_dtype_t dt,
+                            x3d_stream_t stream);
 /* pass 2 (tiny): coefficients of da = A*dpre + B*a + C per (split,channel); dgamma/dbeta += .
  * train=0: BN used running stats (eval) -> A=scale, B=C=0. */
 int x3d_bn_bwd_finalize(const double* stats, int64_t N, int splits, int64_t P, int64_t C, int64_t Cp,

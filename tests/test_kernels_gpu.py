@@ -112,7 +112,14 @@ DW_CASES = [  # N, C, T, H, W, stride, kernel
     (2, 216, 3, 10, 10, 1, (3, 3, 3)),    # 158-pixel multigrid shape, stage 3 (narrow image: 4-wide tiles)
     (2, 432, 2, 5, 5, 1, (3, 3, 3)),      # 158-pixel multigrid shape, stage 4
     (2, 216, 2, 20, 20, 2, (3, 3, 3)),    # 158-pixel multigrid shape, stage 3 entry (20 -> 10)
+    # production sizes (BASELINE config 2 tilings: 112^2 -> 56^2 stride-2 entry, 28^2 stride-1) and X3D-XL widths
+    (2, 54, 16, 112, 112, 2, (3, 3, 3)),
+    (2, 108, 16, 28, 28, 1, (3, 3, 3)),
+    (2, 72, 3, 156, 156, 2, (3, 3, 3)),   # XL stage 1 entry (Cp = 72)
+    (2, 162, 4, 39, 39, 1, (3, 3, 3)),    # XL stage 2 (Cp = 168, odd image)
+    (2, 306, 3, 20, 20, 1, (3, 3, 3)),    # XL stage 3 (Cp = 312)
 ]
+# shapes that must be served by the TMA-tiled kernels (every 3x3x3 case above is a hot shape of some config)
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
@@ -122,6 +129,7 @@ def test_dwconv_fwd_dgrad_wgrad(case, dtype, fused):
     N, C, T, H, W, s, k = case
     Cp = pad8(C)
     splits = 2 if (fused and N % 2 == 0) else 1
+    paths0 = L().path_counts()
     x = O.det_clip((N, C, T, H, W), f'dwx{case}', torch.float32).cuda()
     w = O.det_tensor((C, 1) + k, f'dww{case}', scale=0.4, dtype=torch.float32).cuda()
     xn = to_ndhwc(x, dtype)
@@ -181,6 +189,12 @@ def test_dwconv_fwd_dgrad_wgrad(case, dtype, fused):
              sc.data_ptr() if fused else None, sh.data_ptr() if fused else None, splits, 1 if fused else 0,
              DT[dtype], stream())
     assert rel(dw, w64.grad) < TOL[dtype]
+    # which kernel family served the three calls: 3x3x3 -> TMA-tiled, 5x1x1 -> streaming temporal (never the
+    # shape-generic direct kernels for these hot shapes)
+    d = {kk: v - paths0[kk] for kk, v in L().path_counts().items()}
+    fam = 'tiled' if k == (3, 3, 3) else 'temporal'
+    if k == (3, 3, 3) or not fused:
+        assert d[f'dw_fwd_{fam}'] == 1 and d[f'dw_dgrad_{fam}'] == 1 and d[f'dw_wgrad_{fam}'] == 1, d
 
 
 PW_CASES = [  # N, K, Nout, T, H, W, stride
@@ -194,6 +208,15 @@ PW_CASES = [  # N, K, Nout, T, H, W, stride
     (2, 432, 192, 2, 3, 3, 1),
     (4, 96, 216, 1, 2, 2, 1),      # tiny P: tiles span several samples
     (70, 8, 16, 1, 1, 1, 1),       # P = 1: more than MAXS samples per tile
+    # production size: M = 401 k rows -> 3136 tiles on <= 444 persistent CTAs, statistics flushed per sample
+    (2, 24, 54, 16, 112, 112, 1),
+    (2, 54, 24, 16, 56, 56, 1),
+    # X3D-XL widths (K, N in {72, 136, 162, 280, 306, 630})
+    (2, 72, 162, 4, 39, 39, 1),
+    (2, 306, 136, 2, 20, 20, 1),
+    (2, 280, 630, 2, 10, 10, 1),
+    (2, 630, 280, 2, 10, 10, 1),
+    (2, 32, 72, 3, 40, 40, 2),     # XL downsample branch (K < 64: gathered rows on the tensor-core path)
 ]
 
 
@@ -202,6 +225,7 @@ PW_CASES = [  # N, K, Nout, T, H, W, stride
 def test_pwconv_fwd_dgrad_wgrad(case, dtype):
     N, K, Nn, T, H, W, s = case
     Kp, Np = pad8(K), pad8(Nn)
+    paths0 = L().path_counts()
     x = O.det_clip((N, K, T, H, W), f'pwx{case}', torch.float32).cuda()
     w = O.det_tensor((Nn, K, 1, 1, 1), f'pww{case}', scale=(3.0 / K) ** 0.5, dtype=torch.float32).cuda()
     xn = to_ndhwc(x, dtype)
@@ -238,6 +262,13 @@ def test_pwconv_fwd_dgrad_wgrad(case, dtype):
     L().call('x3d_pwconv_wgrad', xn.data_ptr(), dyn.data_ptr(), dw.data_ptr(), N, T, H, W, K, Kp, Nn, Np, s, DT[dtype],
              stream())
     assert rel(dw, w64.grad.reshape(Nn, K)) < TOL[dtype]
+    d = {kk: v - paths0[kk] for kk, v in L().path_counts().items()}
+    if dtype == torch.bfloat16:      # bf16 storage runs the tcgen05 kernels (fp32 storage is the SIMT parity path)
+        assert d['pw_dgrad_tc'] == 2 and d['pw_dgrad_simt'] == 0, d
+        assert d['pw_fwd_tc'] == 1 or (s == 2 and K >= 64), d
+        assert d['pw_wgrad_tc'] == 1 or s == 2, d
+    else:
+        assert d['pw_fwd_simt'] == 1 and d['pw_wgrad_simt'] == 1, d
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])

@@ -321,10 +321,10 @@ extern "C" int x3d_bn_act_fwd(const void* a, const float* scale, const float* sh
 // =======================================================================================
 // BN backward
 // =======================================================================================
-template <typename T, bool MASK>
+template <typename T, bool MASK, bool STORE>
 __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ mask_out,
-                                     const T* __restrict__ a, double* __restrict__ stats, int64_t P, int Cp, int cv,
-                                     int rows, int64_t chunk) {
+                                     const T* __restrict__ a, double* __restrict__ stats, T* __restrict__ dpre_out,
+                                     int64_t P, int Cp, int cv, int rows, int64_t chunk) {
   x3d::pdl_prologue();
   extern __shared__ float s_acc[];
   ROW_PROLOGUE();
@@ -340,29 +340,43 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __rest
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float dp = (!MASK || m[j] > 0.f) ? d[j] : 0.f;
+      d[j] = dp;
       a0[j] += dp;
       a1[j] = fmaf(dp, x[j], a1[j]);
     }
+    if (STORE) store_vec<T>(dpre_out + off, d);
   }
   block_stats_flush<VEC>(a0, a1, cvec, Cp, s_acc, stats + (int64_t)n * Cp * 2);
 }
-extern "C" int x3d_bn_bwd_reduce(const void* dout, const void* mask_out, const void* a, double* stats,
-                                 int64_t N, int64_t P, int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream) {
+static int bn_bwd_reduce_impl(const void* dout, const void* mask_out, const void* a, double* stats, void* dpre_out,
+                              int64_t N, int64_t P, int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream) {
   X3D_CHECK_ARG(Cp % 8 == 0, "Cp % 8");
   if (N * P == 0) return 0;
+#define RL_(MK, STO)                                                                                         \
+  x3d::launch(bn_bwd_reduce_kernel<T, MK, STO>, grid, g.threads, smem, as_stream(stream), (const T*)dout,       \
+              (const T*)mask_out, (const T*)a, stats, (T*)dpre_out, P, (int)Cp, g.cv, g.rows, g.chunk)
   X3D_DISPATCH_DTYPE(dt, {
     RowGeom g = make_row_geom<T>(N, P, Cp);
     dim3 grid(g.chunks, (unsigned)N);
     size_t smem = (size_t)g.rows * Cp * 2 * sizeof(float);
-    if (mask_out)
-      x3d::launch(bn_bwd_reduce_kernel<T, true>, grid, g.threads, smem, as_stream(stream), 
-          (const T*)dout, (const T*)mask_out, (const T*)a, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
-    else
-      x3d::launch(bn_bwd_reduce_kernel<T, false>, grid, g.threads, smem, as_stream(stream), 
-          (const T*)dout, nullptr, (const T*)a, stats, P, (int)Cp, g.cv, g.rows, g.chunk);
+    if (mask_out && dpre_out) RL_(true, true);
+    else if (mask_out) RL_(true, false);
+    else if (dpre_out) RL_(false, true);
+    else RL_(false, false);
   });
+#undef RL_
   X3D_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int x3d_bn_bwd_reduce(const void* dout, const void* mask_out, const void* a, double* stats,
+                                 int64_t N, int64_t P, int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream) {
+  return bn_bwd_reduce_impl(dout, mask_out, a, stats, nullptr, N, P, Cp, dt, stream);
+}
+extern "C" int x3d_bn_bwd_reduce_store(const void* dout, const void* mask_out, const void* a, double* stats,
+                                       void* dpre_out, int64_t N, int64_t P, int64_t Cp, x3d_dtype_t dt,
+                                       x3d_stream_t stream) {
+  X3D_CHECK_ARG(dpre_out != nullptr, "dpre_out");
+  return bn_bwd_reduce_impl(dout, mask_out, a, stats, dpre_out, N, P, Cp, dt, stream);
 }
 
 // coefficients: da = A*dpre + B*a + Cc.  One thread per channel, loops splits and samples.

@@ -201,11 +201,12 @@ extern "C" int x3d_pwconv_dgrad(const void* dy, const void* wT, void* dx, int64_
   const int64_t P_out = T_ * map.Ho * map.Wo;
   const int64_t M = N * P_out;
   if (M == 0) return 0;
-  if (dt == X3D_BF16 && (stride > 1 || !accumulate)) {
+  if (dt == X3D_BF16) {
     bool handled = false;
-    // strided conv: the dense GEMM rows (nt,ho,wo) land on rows (nt, s*ho, s*wo) of dx (untouched rows keep their value)
+    // strided conv: the dense GEMM rows (nt,ho,wo) land on rows (nt, s*ho, s*wo) of dx (untouched rows keep their value);
+    // accumulate: the epilogue adds to what dx already holds (residual branch gradient)
     const int scatter[6] = {stride, (int)H, (int)W, map.Ho, map.Wo, accumulate};
-    int rc = pwconv_fwd_tc(dy, wT, dx, M, Np, Kp, P_out, nullptr, stride > 1 ? scatter : nullptr, nullptr,
+    int rc = pwconv_fwd_tc(dy, wT, dx, M, Np, Kp, P_out, nullptr, (stride > 1 || accumulate) ? scatter : nullptr, nullptr,
                            as_stream(stream), &handled);
     if (handled) {
       count_path(X3D_PATH_PW_DGRAD_TC);

@@ -827,6 +827,9 @@ int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, 
     p.ss = scatter[0]; p.gH = scatter[1]; p.gW = scatter[2]; p.gHo = scatter[3]; p.gWo = scatter[4];
     p.accum = scatter[5];
     if ((M / ((int64_t)p.gHo * p.gWo)) * p.gH * p.gW >= (1ll << 31)) return 0;
+  } else if (scatter != nullptr) {
+    if (stats != nullptr) return 0;
+    p.accum = scatter[5];                 // dense rows, C += (identity-residual gradient already in dx)
   }
   p.stages = BN > 128 ? 3 : 2;      // small-N layers: 2 stages so that 2-3 CTAs fit per SM (nk is 1-2 there)
   CUtensorMap mapA, mapB;

@@ -1,6 +1,8 @@
 // Stem conv1_s: dense (1,3,3) conv, stride (1,2,2), pad (0,1,1), Ci (<=3) -> Co channels.
 // Reads the user-facing NCDHW fp32 clip directly, writes NDHWC.  Replaces the cuDNN kernel behind
 // nn.Conv3d at x3d.py:196-201 / :317.   TAPS = Ci*9 <= 27.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 using namespace x3d;
@@ -203,6 +205,100 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   }
 }
 
+// ---- wgrad, register-tiled (the one that runs for the stock networks) ------------------------------------
+// dw[co][ci][j][k] += sum_p dy[p][co] * x[n, ci, t, 2ho+j-1, 2wo+k-1].  M = N*T*Ho*Wo is 3.2 M positions at the benchmark
+// shape, the result is a 24 x 27 matrix: the kernel is a skinny reduction that should run at memory speed (x once as
+// fp32 NCDHW, dy once).  Warp = role (input channel ci, group of 8 output channels); its 32 lanes take 32 consecutive
+// output positions of one (n, t) plane, load their 3 x 3 input patch of channel ci straight from the clip (stride-2
+// lanes: every 128-byte line is used by the three k offsets) and one 16-byte vector of dy, and keep the 9 x 8 partial
+// sums in registers over the CTA's whole share of chunks -- no shared-memory staging, 72 FMAs per 10 loads.  All roles
+// of a CTA walk the same chunks, so the patch / dy lines are fetched from L2 once and re-read from L1.  One butterfly
+// reduction per warp at the very end, then one fp32 red per (co, tap) per warp.
+template <typename T, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) stem_wgrad_reg_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                                              float* __restrict__ dw, int Ci, int T_, int H, int W,
+                                                              int Ho, int Wo, int Co, int Cop, int64_t planes,
+                                                              int chunks_per_plane, int64_t nchunks) {
+  x3d::pdl_prologue();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci = warp % Ci, cg = warp / Ci;
+  const int HoWo = Ho * Wo;
+  const int64_t HW = (int64_t)H * W;
+  float2 acc[9][4];
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int64_t plane = ch / chunks_per_plane;            // = n * T + t   (warp-uniform)
+    const int pp = (int)(ch - plane * chunks_per_plane) * 32 + lane;
+    const bool live = pp < HoWo;
+    const int ho = live ? pp / Wo : 0, wo = live ? pp - (pp / Wo) * Wo : 0;
+    const int64_t n = plane / T_;
+    const int t = (int)(plane - n * T_);
+    const float* xp = x + ((n * Ci + ci) * T_ + t) * HW;
+    float xv[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int hh = 2 * ho + j - 1;
+      const bool rok = live && hh >= 0 && hh < H;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int ww = 2 * wo + k - 1;
+        const bool ok = rok && ww >= 0 && ww < W;
+        xv[j * 3 + k] = ok ? __ldg(xp + (int64_t)hh * W + ww) : 0.f;
+      }
+    }
+    float d[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) d[q] = 0.f;
+    if (live) {
+      const T* dp = dy + (plane * HoWo + pp) * Cop + cg * 8;
+      if (sizeof(T) == 2) {
+        float v[8];
+        load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(dp), v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) d[q] = v[q];
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(dp), b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dp) + 4);
+        d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float2 xx = make_float2(xv[i], xv[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(xx, make_float2(d[2 * j], d[2 * j + 1]), acc[i][j]);
+    }
+  }
+  // butterfly reduction over the 32 lanes; afterwards lane l publishes elements l, l+32, l+64 of the 72
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = acc[i][j].x, b = acc[i][j].y;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      acc[i][j] = make_float2(a, b);
+    }
+  const int taps = Ci * 9;
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = i * 8 + 2 * j;                            // element index (tap i, channel 2j / 2j+1)
+      if (lane == (e & 31) || lane == ((e + 1) & 31)) {
+        const bool second = lane != (e & 31);
+        const int c = cg * 8 + 2 * j + (second ? 1 : 0);
+        const float v = second ? acc[i][j].y : acc[i][j].x;
+        if (c < Co && v != 0.f) atomicAdd(&dw[(int64_t)c * taps + ci * 9 + i], v);
+      }
+    }
+}
+
 extern "C" int x3d_stem_conv_s_wgrad(const float* x, const void* dy, float* dw, int64_t N, int64_t Ci, int64_t T_,
                                      int64_t H, int64_t W, int64_t Co, int64_t Cop, x3d_dtype_t dt,
                                      x3d_stream_t stream) {
@@ -211,6 +307,25 @@ extern "C" int x3d_stem_conv_s_wgrad(const float* x, const void* dy, float* dw, 
   const int Ho = (int)((H + 2 - 3) / 2 + 1), Wo = (int)((W + 2 - 3) / 2 + 1);
   const int64_t total = N * T_ * Ho * Wo;
   if (total == 0) return 0;
+  const int roles = (int)(Ci * (Cop / 8));
+  static const bool old_kernel = getenv("X3D_STEM_WGRAD_SMEM") != nullptr;      // A/B switch
+  if (roles <= 12 && (int64_t)Ho * Wo < (1ll << 30) && !old_kernel) {
+    const int cpp = (int)cdiv((int64_t)Ho * Wo, 32);
+    const int64_t planes = N * T_, nchunks = planes * cpp;
+    int64_t blocks = 2 * kNumSMs;
+    if (blocks > nchunks) blocks = nchunks;
+    // <= 9 roles (the stock 3 -> 24 stem): 288 threads at <= 112 registers, two CTAs per SM
+#define SW_(MAXT, MINB)                                                                                          \
+  x3d::launch(stem_wgrad_reg_kernel<T, MAXT, MINB>, (unsigned)blocks, roles * 32, 0, as_stream(stream), x, (const T*)dy, \
+              dw, (int)Ci, (int)T_, (int)H, (int)W, Ho, Wo, (int)Co, (int)Cop, planes, cpp, nchunks)
+    X3D_DISPATCH_DTYPE(dt, {
+      if (roles <= 9) SW_(288, 2);
+      else SW_(384, 1);
+    });
+#undef SW_
+    X3D_LAUNCH_CHECK();
+    return 0;
+  }
   int64_t blocks = 4 * kNumSMs;
   int64_t ppb = cdiv(cdiv(total, blocks), SW_POS) * SW_POS;
   blocks = cdiv(total, ppb);

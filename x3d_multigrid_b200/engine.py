@@ -462,7 +462,23 @@ class Engine:
                 ev_dad.record(self.side)
         # ---- bn3 backward (dpre = dout * [out > 0])
         da3 = self._act(N, T, Ho, Wo, Cop)
-        self._bn_backward(ab, pre + '.bn3', bn3, dout, out, a3, N, P_out, Co, Cop, da3)
+        dx = None
+        if blk.downsample is None and need_dx:
+            # identity residual (x3d.py:168-169): dx = dpre + conv1-dgrad.  The reduce pass writes dpre straight into
+            # the dx buffer (same shape as dout), the apply pass reads it unmasked, and the conv1 dgrad at the end of
+            # this function accumulates on top -- no separate "dx += dout*(out>0)" pass, one tensor read less per pass
+            dx = self._act(N, T, H, W, Cinp)
+            bst3 = self._stats(ab, N, Cop)
+            lib.call('x3d_bn_bwd_reduce_store', _ptr(dout), _ptr(out), _ptr(a3), _ptr(bst3), _ptr(dx), N, P_out, Cop,
+                     dt, st)
+            coef3 = self._f32(3, bn3.splits, Cop)
+            lib.call('x3d_bn_bwd_finalize', _ptr(bst3), N, bn3.splits, P_out, Co, Cop, self.p(pre + '.bn3.weight'),
+                     _ptr(bn3.mean), _ptr(bn3.rstd), int(bn3.train), _ptr(coef3), self.g(pre + '.bn3.weight'),
+                     self.g(pre + '.bn3.bias'), st)
+            lib.call('x3d_bn_bwd_apply', _ptr(dx), None, _ptr(a3), _ptr(coef3), bn3.splits, _ptr(da3), N, P_out, Cop,
+                     dt, st)
+        else:
+            self._bn_backward(ab, pre + '.bn3', bn3, dout, out, a3, N, P_out, Co, Cop, da3)
         # ---- conv3
         self._wgrad('x3d_pwconv_wgrad', (v, da3), _ptr(v), _ptr(da3), self.g(pre + '.conv3.weight'), N, T, Ho, Wo, Cm,
                     Cmp, Co, Cop, 1, dt)
@@ -509,10 +525,11 @@ class Engine:
         # ---- conv1
         self._wgrad('x3d_pwconv_wgrad', (x, da1), _ptr(x), _ptr(da1), self.g(pre + '.conv1.weight'), N, T, H, W, Cin,
                     Cinp, Cm, Cmp, 1, dt)
-        dx = None
         if need_dx:
-            dx = self._act(N, T, H, W, Cinp)
-            lib.call('x3d_pwconv_dgrad', _ptr(da1), self.pk(pre + '.conv1.t'), _ptr(dx), N, T, H, W, Cinp, Cmp, 1, 0,
+            acc1 = 1 if dx is not None else 0        # identity block: dx already holds dpre
+            if dx is None:
+                dx = self._act(N, T, H, W, Cinp)
+            lib.call('x3d_pwconv_dgrad', _ptr(da1), self.pk(pre + '.conv1.t'), _ptr(dx), N, T, H, W, Cinp, Cmp, 1, acc1,
                      dt, st)
         # ---- residual branch
         if blk.downsample is not None:
@@ -523,8 +540,6 @@ class Engine:
             if need_dx:
                 lib.call('x3d_pwconv_dgrad', _ptr(dad), self.pk(pre + '.downsample.0.t'), _ptr(dx), N, T, H, W, Cinp,
                          Cop, s, 1, dt, st)
-        elif need_dx:
-            lib.call('x3d_relu_bwd_add', _ptr(dout), _ptr(out), _ptr(dx), dx.numel(), dt, st)
         return dx
 
     # ------------------------------------------------------------------ head
