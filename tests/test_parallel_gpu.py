@@ -1,0 +1,123 @@
+"""Data-parallel correctness: N ranks with per-replica BatchNorm and a mean-over-global-batch loss
+(train_x3d_kinetics_multigrid.py:175-177,259-279) must give the gradients / parameter update of ONE rank that sees the
+concatenated batch with S = s*G BN splits, where the batch is permuted so that the BN groups coincide.
+
+* test_two_replicas_equal_one_rank_with_more_splits -- the arithmetic, on one GPU (two replicas run one after the other,
+  their gradients averaged on the host): always runs.
+* test_two_nccl_ranks_match_single_rank -- the real thing over NCCL on 2 GPUs, in all three execution modes (eager
+  bucketed allreduce, fully captured step incl. NCCL, captured fwd/bwd + eager allreduce): needs 2 GPUs."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import x3d_oracle as O
+from dp_worker import shard_rows
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def _model(ncls, splits, dev='cuda:0'):
+    import x3d_multigrid_b200 as X
+    m = X.generate_model('S', n_classes=ncls, base_bn_splits=splits, dropout=0.0)
+    sd = O.make_state_dict('S', ncls, splits)
+    m.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in sd.items()})
+    return m.to(dev).set_compute_dtype(torch.float32).train()
+
+
+def _single_rank_reference(world, per_rank, s, ncls=7, lr=0.05):
+    """one process, whole batch, S = s*world splits: (loss, grads, updated params, running stats)"""
+    from x3d_multigrid_b200.optim import FusedSGD
+    B = per_rank * world
+    m = _model(ncls, s * world)
+    xg = O.det_clip((B, 3, 4, 32, 32), 'dpclip', torch.float32).cuda()
+    yg = (torch.arange(B) * 3 % ncls).view(B, 1).cuda()
+    opt = FusedSGD(m.parameters(), lr=lr, momentum=0.9, weight_decay=5e-5)
+    loss = torch.nn.functional.cross_entropy(m(xg), yg)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    opt.step()
+    torch.cuda.synchronize()
+    return float(loss), grads, {k: p.detach().clone() for k, p in m.named_parameters()}, dict(m.named_buffers()), xg, yg
+
+
+def _grade(got, want, what):
+    """whole-network train-mode-BN gradients are ill conditioned (two legal fp32 executions of the
+    reference differ by ~1e-2): heads tight, everything bounded, the bulk small"""
+    errs = sorted(((rel(got[k], want[k]), k) for k in want), reverse=True)
+    med = errs[len(errs) // 2][0]
+    print(f'{what}: worst {errs[0][1]} {errs[0][0]:.2e}, median {med:.2e}')
+    for k in ('fc2.bias', 'fc2.weight', 'fc1.weight'):
+        assert rel(got[k], want[k]) < 1e-4, (what, k)
+    assert errs[0][0] < 5e-2 and med < 5e-3, (what, errs[:3])
+
+
+def test_two_replicas_equal_one_rank_with_more_splits():
+    world, per_rank, s, ncls = 2, 4, 2, 7
+    loss1, g1, p1, bufs1, xg, yg = _single_rank_reference(world, per_rank, s)
+    acc, losses = {}, []
+    for r in range(world):
+        rows = shard_rows(r, world, per_rank, s)
+        m = _model(ncls, s)
+        loss = torch.nn.functional.cross_entropy(m(xg[rows]), yg[rows])
+        loss.backward()
+        losses.append(float(loss))
+        for k, p in m.named_parameters():
+            acc[k] = p.grad / world if k not in acc else acc[k] + p.grad / world
+        # per-replica BN: local split b of rank r is global split r*s + b
+        C = m.bn1.num_features
+        mine = m.bn1.split_bn.running_mean.view(s, C)
+        ref = bufs1['bn1.split_bn.running_mean'].view(s * world, C)[r * s:(r + 1) * s]
+        assert rel(mine, ref) < 1e-5
+        C = m.layer3[0].bn2.num_features
+        mine = m.layer3[0].bn2.split_bn.running_var.view(s, C)
+        ref = bufs1['layer3.0.bn2.split_bn.running_var'].view(s * world, C)[r * s:(r + 1) * s]
+        assert rel(mine, ref) < 1e-4
+    assert abs(sum(losses) / world - loss1) < 1e-5
+    _grade(acc, g1, 'mean of replica gradients vs one rank with S=s*G splits')
+
+
+def _free_port():
+    sk = socket.socket()
+    sk.bind(('127.0.0.1', 0))
+    p = sk.getsockname()[1]
+    sk.close()
+    return p
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+@pytest.mark.parametrize('mode', ['eager', 'graph', 'graph_tail'])
+def test_two_nccl_ranks_match_single_rank(mode, tmp_path):
+    world, per_rank, s = 2, 4, 2
+    port = _free_port()
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, 'tests', 'dp_worker.py'), str(r), str(world),
+                               str(port), mode, str(tmp_path)]) for r in range(world)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    outs = [torch.load(os.path.join(tmp_path, f'{mode}_{r}.pt')) for r in range(world)]
+    loss1, g1, p1, bufs1, _, _ = _single_rank_reference(world, per_rank, s)
+    # both ranks hold the same averaged gradients and the same updated parameters
+    assert torch.equal(outs[0]['gflat'], outs[1]['gflat'])
+    for k in p1:
+        assert torch.equal(outs[0]['params'][k], outs[1]['params'][k]), k
+    assert abs((outs[0]['loss'] + outs[1]['loss']) / 2 - loss1) < 1e-5
+    got = {k: outs[0]['gflat'][o:o + n].view(g1[k].shape) for k, (o, n) in outs[0]['goff'].items()}
+    _grade(got, g1, f'{mode}: allreduced gradients vs single rank')
+    upd_got = {k: outs[0]['params'][k].double() - O.make_state_dict('S', 7, s)[k].double() for k in p1}
+    upd_ref = {k: p1[k].double().cpu() - O.make_state_dict('S', 7, s)[k].double() for k in p1}
+    _grade(upd_got, upd_ref, f'{mode}: parameter update vs single rank')
+    # BN buffers stay per replica
+    for r in range(world):
+        C = 24
+        mine = outs[r]['stats']['bn1.split_bn.running_mean'].view(s, C)
+        ref = bufs1['bn1.split_bn.running_mean'].view(s * world, C)[r * s:(r + 1) * s]
+        assert rel(mine, ref) < 1e-5

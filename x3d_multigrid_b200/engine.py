@@ -108,9 +108,21 @@ class Engine:
         self._sig = None
         self.arena_f: Optional[Arena] = None
         self.arena_b: Optional[Arena] = None
-        self.side = None
-        self.use_side = True        # parallel.DistributedX3D switches it off (see there)
+        self._side = None
+        self.use_side = True        # parallel.DistributedX3D switches it off in eager mode (see there)
         self.grad_hook: Optional[Callable[[int], None]] = None   # called after each bucket's grads are final
+
+    @property
+    def side(self):
+        """second stream for work that feeds nothing downstream (weight gradients, the downsample branch)"""
+        return self._side if self.use_side else None
+
+    @side.setter
+    def side(self, value):        # bench.py's per-kernel timing parks the stream (None) and puts it back
+        if value is None:
+            self.use_side = False
+        else:
+            self._side, self.use_side = value, True
 
     # ------------------------------------------------------------------ parameter tables
     def _stream(self):
@@ -133,8 +145,7 @@ class Engine:
         self.arena_f, self.arena_b = Arena(device), Arena(device)
         # weight-gradient kernels feed nothing downstream: they run on a side stream, concurrently with the
         # dgrad / BN chain of the main stream (fills the SMs that the small late-stage kernels leave idle)
-        self.side = torch.cuda.Stream(device) if (device.type == 'cuda' and self.use_side and
-                                                  not os.environ.get('X3D_NO_SIDE')) else None
+        self._side = torch.cuda.Stream(device) if (device.type == 'cuda' and not os.environ.get('X3D_NO_SIDE')) else None
 
         # ---- flat gradient buffer, bucket order: head+stage4 first ... stem last
         named = dict(m.named_parameters())

@@ -33,24 +33,32 @@ class BucketReducer:
         if hi > lo:
             self.works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
-    def finish(self, flat: torch.Tensor):
-        """wait for every bucket, then scale to the mean"""
+    def finish(self, flat: torch.Tensor, scale: bool = True):
+        """wait for every bucket, then scale to the mean (``scale=False``: the optimizer applies 1/world)"""
         if self.world == 1:
             return
         for w in self.works:
             w.wait()
         self.works = []
-        flat.mul_(1.0 / self.world)
+        if scale:
+            flat.mul_(1.0 / self.world)
 
 
 class DistributedX3D(torch.nn.Module):
     """``DistributedX3D(model)`` -- drop-in for ``nn.DataParallel(model)`` in the reference loop
     (keeps the ``.module`` attribute the scripts use, train_x3d_kinetics_multigrid.py:205,228,287)."""
 
-    def __init__(self, module, process_group=None, broadcast_from: Optional[int] = 0):
+    def __init__(self, module, process_group=None, broadcast_from: Optional[int] = 0, side_stream: bool = False,
+                 defer_scale: bool = False):
+        """``side_stream``: keep the weight-gradient kernels on the engine's second stream while the bucket
+        allreduces are in flight (used by the CUDA-graph step, where the whole step -- NCCL kernels included -- is
+        one captured graph); ``defer_scale``: leave the 1/world factor to the optimizer (FusedSGD.grad_scale)
+        instead of a separate pass over the flat gradient buffer."""
         super().__init__()
         self.module = module
         self.group = process_group
+        self.side_stream = side_stream
+        self.defer_scale = defer_scale
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         if self.world > 1 and broadcast_from is not None:
             for t in list(module.parameters()) + list(module.buffers()):
@@ -66,15 +74,14 @@ class DistributedX3D(torch.nn.Module):
         # 2 GPUs: early-launched dependents and NCCL compete for the same SM slots), each alone is fine -- this mode
         # keeps PDL and runs the weight gradients on the main stream.  (Graph mode, bench.py's default, replays
         # forward+backward without any NCCL kernel in flight and keeps both.)
-        eng.use_side = False
-        eng.side = None
+        eng.use_side = bool(self.side_stream)
 
         def hook(bucket: int, eng=eng):
             if self._reducer is None or self._reducer.ranges != eng.bucket_ranges:
                 self._reducer = BucketReducer(eng.bucket_ranges, self.group)
             self._reducer.launch(eng.gflat, bucket)
             if bucket == len(eng.bucket_ranges) - 1:
-                self._reducer.finish(eng.gflat)
+                self._reducer.finish(eng.gflat, scale=not self.defer_scale)
 
         eng.grad_hook = hook
 
