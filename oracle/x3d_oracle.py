@@ -22,6 +22,9 @@ Two convolution back-ends restate the same math:
   * ``conv_impl="explicit"`` -- shifted-slice sums / matmul, no conv library;
   * ``conv_impl="aten"``     -- ``torch.nn.functional.conv3d``, i.e. exactly the
     ATen call the reference's ``nn.Conv3d`` modules make (used for CPU timing).
+``bn_impl="aten"`` additionally issues the reference's exact BatchNorm / Swish calls
+(``F.batch_norm`` on the ``(n//s, c*s, ...)`` view + the two affine ops, x3d.py:50-57; the
+saved-x ``SwishEfficient`` backward, :71-84) -- the op sequence the timing arms must execute.
 """
 from __future__ import annotations
 
@@ -192,11 +195,56 @@ def stem_conv_s(x, w, conv_impl='explicit'):
     return y
 
 
-def sub_bn(x, prefix, sd, splits: int, training: bool, new_stats: Optional[dict]):
+def sub_bn_aten(x, prefix, sd, splits: int, training: bool, new_stats: Optional[dict]):
+    """SubBatchNorm3d.forward with the reference's exact ATen calls (x3d.py:47-58): F.batch_norm on the
+    (n//s, c*s, t, h, w) view with running buffers, then the two elementwise affine ops.  Same math as ``sub_bn``;
+    used where the reference's op sequence matters (CPU / GPU timing arms of bench.py)."""
+    gamma, beta = sd[prefix + '.weight'], sd[prefix + '.bias']
+    N, C = x.shape[:2]
+    if training:
+        rm = sd.get(prefix + '.split_bn.running_mean')
+        rv = sd.get(prefix + '.split_bn.running_var')
+        if rm is None or rm.numel() != splits * C:
+            rm = torch.zeros(splits * C, dtype=x.dtype, device=x.device)
+            rv = torch.ones(splits * C, dtype=x.dtype, device=x.device)
+        rm, rv = rm.detach().clone().to(torch.float32 if x.dtype != torch.float64 else x.dtype), \
+            rv.detach().clone().to(torch.float32 if x.dtype != torch.float64 else x.dtype)
+        y = F.batch_norm(x.view(N // splits, C * splits, *x.shape[2:]), rm, rv, None, None, True, BN_MOMENTUM, BN_EPS)
+        y = y.view(x.shape)
+        if new_stats is not None:
+            new_stats[prefix + '.split_bn.running_mean'] = rm
+            new_stats[prefix + '.split_bn.running_var'] = rv
+    else:
+        y = F.batch_norm(x, sd[prefix + '.bn.running_mean'], sd[prefix + '.bn.running_var'], None, None, False,
+                         BN_MOMENTUM, BN_EPS)
+    y = y * gamma.view(-1, 1, 1, 1)
+    y = y + beta.view(-1, 1, 1, 1)
+    return y
+
+
+class _SwishEfficient(torch.autograd.Function):
+    """x3d.py:71-84: saves x, hand-written backward"""
+
+    @staticmethod
+    def forward(ctx, x):
+        result = x * torch.sigmoid(x)
+        ctx.save_for_backward(x)
+        return result
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (x,) = ctx.saved_tensors
+        sigmoid_x = torch.sigmoid(x)
+        return grad_output * (sigmoid_x * (1 + x * (1 - sigmoid_x)))
+
+
+def sub_bn(x, prefix, sd, splits: int, training: bool, new_stats: Optional[dict], impl: str = 'explicit'):
     """SubBatchNorm3d.forward, x3d.py:47-58.  Training: split b = samples b::s
     (the reference's NCDHW view (n//s, c*s, ...)), biased variance, then the
     shared affine.  Running statistics are returned through ``new_stats``
     (momentum 0.1, unbiased variance; index b*C+c) instead of being mutated."""
+    if impl == 'aten':
+        return sub_bn_aten(x, prefix, sd, splits, training, new_stats)
     gamma, beta = sd[prefix + '.weight'], sd[prefix + '.bias']
     N, C = x.shape[:2]
     if training:
@@ -241,13 +289,13 @@ def swish(x):
 
 
 def bottleneck(x, prefix, sd, stride, has_se, has_ds, splits, training, new_stats, conv_impl,
-               taps: Optional[dict] = None):
+               taps: Optional[dict] = None, bn_impl: str = 'explicit'):
     """Bottleneck.forward, x3d.py:143-171."""
     out = pwconv(x, sd[prefix + '.conv1.weight'], 1, None, conv_impl)
-    out = sub_bn(out, prefix + '.bn1', sd, splits, training, new_stats)
+    out = sub_bn(out, prefix + '.bn1', sd, splits, training, new_stats, bn_impl)
     out = torch.relu(out)
     out = dwconv3d(out, sd[prefix + '.conv2.weight'], stride, conv_impl)
-    out = sub_bn(out, prefix + '.bn2', sd, splits, training, new_stats)
+    out = sub_bn(out, prefix + '.bn2', sd, splits, training, new_stats, bn_impl)
     if has_se:
         se = out.mean(dim=(2, 3, 4), keepdim=True)
         se = pwconv(se, sd[prefix + '.fc1.weight'], 1, sd[prefix + '.fc1.bias'], conv_impl)
@@ -255,12 +303,12 @@ def bottleneck(x, prefix, sd, stride, has_se, has_ds, splits, training, new_stat
         se = pwconv(se, sd[prefix + '.fc2.weight'], 1, sd[prefix + '.fc2.bias'], conv_impl)
         se = torch.sigmoid(se)
         out = out * se
-    out = swish(out)
+    out = _SwishEfficient.apply(out) if bn_impl == 'aten' else swish(out)
     out = pwconv(out, sd[prefix + '.conv3.weight'], 1, None, conv_impl)
-    out = sub_bn(out, prefix + '.bn3', sd, splits, training, new_stats)
+    out = sub_bn(out, prefix + '.bn3', sd, splits, training, new_stats, bn_impl)
     if has_ds:
         res = pwconv(x, sd[prefix + '.downsample.0.weight'], stride, None, conv_impl)
-        res = sub_bn(res, prefix + '.downsample.1', sd, splits, training, new_stats)
+        res = sub_bn(res, prefix + '.downsample.1', sd, splits, training, new_stats, bn_impl)
     else:
         res = x
     out = torch.relu(out + res)
@@ -271,20 +319,20 @@ def bottleneck(x, prefix, sd, stride, has_se, has_ds, splits, training, new_stat
 
 def forward(sd, x, version='M', splits=1, training=True, dropout_mask=None, task='class',
             conv_impl='explicit', widen_factor=1.0, new_stats: Optional[dict] = None,
-            taps: Optional[dict] = None):
+            taps: Optional[dict] = None, bn_impl: str = 'explicit'):
     """ResNet.forward, x3d.py:316-345.  ``dropout_mask`` ([B,2048] or [B,T,2048],
     already scaled by 1/(1-p)) replaces nn.Dropout's RNG; None = no dropout."""
     out = stem_conv_s(x, sd['conv1_s.weight'], conv_impl)
     out = dwconv3d(out, sd['conv1_t.weight'], 1, conv_impl)
-    out = sub_bn(out, 'bn1', sd, splits, training, new_stats)
+    out = sub_bn(out, 'bn1', sd, splits, training, new_stats, bn_impl)
     out = torch.relu(out)
     if taps is not None:
         taps['stem'] = out
     for (prefix, _cin, _mid, _cout, stride, has_se, has_ds) in block_specs(version, widen_factor):
         out = bottleneck(out, prefix, sd, stride, has_se, has_ds, splits, training, new_stats,
-                         conv_impl, taps)
+                         conv_impl, taps, bn_impl)
     out = pwconv(out, sd['conv5.weight'], 1, None, conv_impl)
-    out = sub_bn(out, 'bn5', sd, splits, training, new_stats)
+    out = sub_bn(out, 'bn5', sd, splits, training, new_stats, bn_impl)
     out = torch.relu(out)
     if task == 'class':
         out = out.mean(dim=(2, 3, 4), keepdim=True)

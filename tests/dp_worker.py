@@ -16,6 +16,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+CROP = 96      # stage-4 BN groups then hold 2 x 4 x 3 x 3 = 72 values (tiny groups make the gradients pure noise)
 
 
 def shard_rows(rank, world, per_rank, local_splits):
@@ -43,7 +44,7 @@ def main(rank, world, port, mode, outdir, per_rank=4, local_splits=2, dtype='fp3
     m.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in sd.items()})
     m = m.to(dev).set_compute_dtype(torch.float32 if dtype == 'fp32' else torch.bfloat16).train()
     B = per_rank * world
-    xg = O.det_clip((B, 3, 4, 32, 32), 'dpclip', torch.float32)
+    xg = O.det_clip((B, 3, 4, CROP, CROP), 'dpclip', torch.float32)
     yg = (torch.arange(B) * 3 % ncls).view(B, 1)
     rows = shard_rows(rank, world, per_rank, local_splits)
     x, y = xg[rows].to(dev), yg[rows].to(dev)
@@ -61,12 +62,12 @@ def main(rank, world, port, mode, outdir, per_rank=4, local_splits=2, dtype='fp3
         opt.grad_scale = 1.0 / world
         step = GraphedTrainStep(net, opt, crit, x, y)          # preserve_state: warm-up steps are undone
         loss = step(x, y)
-        grads = m.engine().gflat.clone() / world
+        grads = step.flat.clone() / world
     else:
         opt.grad_scale = 1.0 / world
-        step = GraphedTrainStep(m, opt, crit, x, y, reduce_fn=lambda: dist.all_reduce(m.engine().gflat))
+        step = GraphedTrainStep(m, opt, crit, x, y, reduce_fn=lambda flat: dist.all_reduce(flat))
         loss = step(x, y)
-        grads = m.engine().gflat.clone() / world
+        grads = step.flat.clone() / world
     torch.cuda.synchronize()
     eng = m.engine()
     out = {'loss': float(loss), 'gflat': grads.cpu(),

@@ -239,12 +239,22 @@ class Engine:
     def p(self, name):
         return self.refs[name].param.data_ptr()
 
+    def _gflat_has_outside_views(self) -> bool:
+        """does anybody else hold a view of the flat gradient buffer?  (.grad of the parameters after a backward pass,
+        or gradients an earlier backward of the SAME autograd graph has returned and autograd has not yet accumulated,
+        e.g. (loss1 + loss2).backward() over two forward passes)"""
+        try:
+            # the tensor itself + the temporary storage handle made here = 2
+            return torch._C._storage_Use_Count(self.gflat.untyped_storage()._cdata) > 2
+        except Exception:       # private API missing: be conservative
+            return True
+
     def new_grad_buffer(self):
-        """Zeroed flat gradient buffer for this backward pass.  The persistent buffer is reused
-        (stable addresses: fused optimizer tables and CUDA graphs stay valid) unless some
-        parameter still holds a .grad -- then the caller is accumulating and the old buffer may
-        be aliased by those .grad views, so a fresh one is taken."""
-        if any(r.param.grad is not None for r in self.param_order):
+        """Zeroed flat gradient buffer for this backward pass.  The persistent buffer is reused (stable addresses:
+        fused optimizer tables and CUDA graphs stay valid) unless views of it are still alive outside the engine --
+        then a caller is accumulating, or autograd still owes the previous result to the parameters, and a fresh
+        buffer is taken (whoever holds the old views keeps the old buffer alive)."""
+        if self._gflat_has_outside_views():
             self.gflat = torch.zeros(self.gflat_numel, dtype=torch.float32, device=self.device)
         else:
             self.gflat.zero_()

@@ -14,9 +14,15 @@ every replay, so ``lr_sched.step()`` of the reference loop (train_x3d_kinetics_m
 Building a step runs ``warmup`` real training steps on the example batch; by default the parameters, BN
 buffers and momentum buffers are restored afterwards (``preserve_state=True``).
 
-Data parallel: pass ``reduce_fn`` (e.g. ``lambda: dist.all_reduce(model.engine().gflat)``).  The graph then holds
-forward + backward only; the gradient allreduce (one NCCL call on the flat 15 MB buffer, ~0.1 ms over NVLink) and
-the one-kernel optimizer step run eagerly after the replay -- NCCL work is never captured."""
+Data parallel, two ways:
+* wrap the model in ``parallel.DistributedX3D(model, side_stream=True, defer_scale=True)`` and set
+  ``optimizer.grad_scale = 1/world``: the bucket allreduces are issued from inside the backward pass and the WHOLE
+  step -- NCCL kernels and the SGD kernel included -- is captured; a replay overlaps every bucket's allreduce with
+  the backward pass of the earlier stages, nothing runs from the host between the first and the last kernel;
+* or pass ``reduce_fn(flat)`` (e.g. ``lambda flat: dist.all_reduce(flat)``): the graph then holds forward + backward
+  only; one NCCL call on the flat gradient buffer and the one-kernel optimizer step run eagerly after the replay.
+  ``flat`` is the gradient buffer THIS graph was captured with (the engine may move on to another buffer when eager
+  steps run in between)."""
 from __future__ import annotations
 
 import torch
@@ -51,6 +57,10 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.static_loss = self._one_step(captured=True)
         torch.cuda.synchronize(dev)
+        # everything the captured kernels address must outlive the graph: the flat gradient buffer belongs to the
+        # engine, which replaces it when an eager backward finds views of it still alive (Engine.new_grad_buffer)
+        net = getattr(self.model, 'module', self.model)
+        self.flat = net.engine().gflat if hasattr(net, 'engine') else None
         if snap is not None:
             self._restore(snap)
 
@@ -88,7 +98,11 @@ class GraphedTrainStep:
 
     def _finish(self):
         """eager tail of a data-parallel step: gradient allreduce + optimizer"""
-        self.reduce_fn()
+        net = getattr(self.model, 'module', self.model)
+        flat = getattr(self, 'flat', None)
+        if flat is None and hasattr(net, 'engine'):
+            flat = net.engine().gflat              # warm-up steps before the capture
+        self.reduce_fn(flat)
         self.opt.step()
 
     def __call__(self, x, y):

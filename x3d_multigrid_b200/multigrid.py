@@ -228,7 +228,8 @@ class MultigridTrainer:
         loss = self.crit(self.model(x), y)
         loss.backward()
         if self.reduce_fn is not None:
-            self.reduce_fn()
+            net = getattr(self.model, 'module', self.model)
+            self.reduce_fn(net.engine().gflat)
         self.opt.step()
         return loss.detach()
 
