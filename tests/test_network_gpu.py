@@ -106,7 +106,7 @@ def _run_net(case, dtype):
     return m, sd, gold, x, labels, logits, loss
 
 
-def _check_golden_grads(m, gold, floor, factor_of=None, factor=3.0):
+def _check_golden_grads(m, gold, floor, factor_of=None, factor=2.0):
     """parameter gradients against what the REFERENCE produced (golden): first 16 entries + norm of every
     parameter, and the full tensors stored under gfull/.  Bound: `floor`, or `factor` x the reference-fp32 error
     of the same parameter (`factor_of`, SURVEY 4.1 protocol item 3) where given."""
@@ -116,8 +116,11 @@ def _check_golden_grads(m, gold, floor, factor_of=None, factor=3.0):
         e = rel(p.grad.reshape(-1)[:16], gold['ghead/' + k])
         en = abs(float(p.grad.double().norm()) - float(gold['gnorm/' + k])) / (float(gold['gnorm/' + k]) + 1e-300)
         worst.append((max(e, en), k))
-        # 16 entries are a noisier sample of the same rounding noise than the whole tensor: twice the bound
-        assert e <= 2 * bound and en <= bound, (k, e, en, bound)
+        assert en <= bound, (k, en, bound)
+        # 16 entries of a deep parameter are a far noisier sample of the rounding noise than its norm or the whole
+        # tensor (gfull below): graded for the head parameters only, where no BN backward amplifies anything
+        if k.split('.')[0] in ('fc2', 'fc1', 'bn5'):
+            assert e <= bound, (k, e, bound)
         if 'gfull/' + k in gold.files:
             ef = rel(p.grad, gold['gfull/' + k])
             assert ef <= bound, (k, ef, bound)
@@ -171,10 +174,9 @@ def test_network_fp32_matches_reference_golden(case):
         err_ref = rel(g32[k], g64[k])
         eref[k] = err_ref
         report.append((err_new, err_ref, k))
-        # factor 3: err_ref is ONE sample of the fp32 rounding noise of the reference; the kernels' own run-to-run
-        # noise (fp32 atomics order in the statistics / weight-gradient reductions) reaches 2.2x of it about once in
-        # 15 runs on these tiny clips (measured), so 2x flickers
-        assert err_new <= max(1e-4, 3 * err_ref), (k, err_new, err_ref)
+        # factor 2 (SURVEY 4.1 protocol item 3): err_ref is one sample of the fp32 rounding noise of the reference;
+        # the CUDA path is run-to-run reproducible (test_run_to_run_reproducibility), so this does not flicker
+        assert err_new <= max(1e-4, 2 * err_ref), (k, err_new, err_ref)
     report.sort(reverse=True)
     print(f'fp32 [{case}] worst param-grad errors vs fp64 (ours, reference-fp32): '
           + ', '.join(f'{k}: {a:.1e}/{b:.1e}' for a, b, k in report[:4]))
@@ -336,14 +338,14 @@ def test_multigrid_trainer_graphs_match_eager_and_oracle_schedule():
     # SURVEY.md 4.1), so graph-vs-eager is graded on the well-conditioned quantities: the losses, the update of the
     # classifier bias (3 warm-up steps of a capture that were not undone, a stale momentum buffer or a missed LR
     # change would change it by O(1)) and the stem's running statistics.
-    assert np.allclose(lg, le, rtol=5e-2), (lg, le)
+    assert np.allclose(lg, le, rtol=2e-3), (lg, le)
     sg, se = mg.state_dict(), me.state_dict()
     assert set(sg) == set(se)
     for k in sg:
         if not sg[k].is_floating_point():
             assert torch.equal(sg[k], se[k]), k
     d_g, d_e = sg['fc2.bias'].double().cpu() - sd0['fc2.bias'].double(), se['fc2.bias'].double().cpu() - sd0['fc2.bias'].double()
-    assert rel(d_g, d_e) < 0.1, rel(d_g, d_e)
+    assert rel(d_g, d_e) < 2e-2, rel(d_g, d_e)
     assert rel(sg['bn1.split_bn.running_var'], se['bn1.split_bn.running_var']) < 2e-2
     assert torch.allclose(sg['bn1.split_bn.running_mean'], se['bn1.split_bn.running_mean'], atol=2e-5, rtol=5e-2)
     # the BN split count follows the long cycle (base 1 x LONG_CYCLE[2] = 2 at the end)
@@ -389,9 +391,14 @@ def test_config2_bf16_matches_reference_golden():
     assert abs(loss.item() - float(gold['loss'])) < 2e-2 * float(gold['loss'])
     assert wv < 2e-2 and wm < 2e-2
     # head gradients (no BN backward between them and the loss) at the bf16 tolerance
-    for k in ('fc2.bias', 'fc2.weight', 'fc1.weight'):
-        p = dict(m.named_parameters())[k]
-        assert rel(p.grad.reshape(-1)[:16], gold['ghead/' + k]) < 2e-2, k
+    pn = dict(m.named_parameters())
+    for k in ('fc2.bias', 'fc2.weight'):
+        assert rel(pn[k].grad.reshape(-1)[:16], gold['ghead/' + k]) < 2e-2, k
+    # fc1.weight[0, :16] = sum_b dz[b, 0] * pooled[b, :16] cancels over the batch: a few 1e-2 in any bf16 execution
+    e1 = rel(pn['fc1.weight'].grad.reshape(-1)[:16], gold['ghead/fc1.weight'])
+    n1 = abs(float(pn['fc1.weight'].grad.double().norm()) - float(gold['gnorm/fc1.weight'])) / float(gold['gnorm/fc1.weight'])
+    print(f'config2 bf16: fc1.weight grad head err {e1:.2e}, norm err {n1:.2e}')
+    assert e1 < 0.15 and n1 < 2e-2
     for p in m.parameters():
         assert torch.isfinite(p.grad).all()
     # eval path on the aggregated statistics
@@ -416,9 +423,11 @@ def test_config2_batch4_fp32_matches_reference_golden():
     # head gradients are well conditioned; the deep ones carry the train-mode-BN amplification: report
     for k in ('fc2.bias', 'fc2.weight', 'fc1.weight', 'bn5.weight', 'bn5.bias'):
         p = dict(m.named_parameters())[k]
-        assert rel(p.grad.reshape(-1)[:16], gold['ghead/' + k]) < 1e-4, k
-    errs = sorted(((rel(p.grad.reshape(-1)[:16], gold['ghead/' + k]), k) for k, p in m.named_parameters()), reverse=True)
-    print('config2 b4 fp32: worst ghead errors ' + ', '.join(f'{k} {e:.1e}' for e, k in errs[:4]))
+        # bn5's gradients are sums of 50 k signed terms per channel (cancellation): a few 1e-4 in fp32
+        assert rel(p.grad.reshape(-1)[:16], gold['ghead/' + k]) < (1e-3 if k.startswith('bn5') else 1e-4), k
+    errs = sorted(((abs(float(p.grad.double().norm()) - float(gold['gnorm/' + k])) / (float(gold['gnorm/' + k]) + 1e-300), k)
+                   for k, p in m.named_parameters()), reverse=True)
+    print('config2 b4 fp32: worst gradient-norm errors ' + ', '.join(f'{k} {e:.1e}' for e, k in errs[:4]))
     assert errs[0][0] < 5e-2          # reference fp32 vs fp64 is ~1e-2 on these
     m.aggregate_sub_bn_stats()
     m.eval()
@@ -521,18 +530,30 @@ def test_two_forwards_before_backward():
     (l1 + l2).backward()
     for k, p in m.named_parameters():
         assert rel(p.grad, want[k]) < 1e-5, k
-    # train mode (split statistics saved by the SE blocks come from the arena): forward of x2 must not corrupt x1's
+    # train mode (the per-sample statistics the SE blocks save for backward come from the arena): a forward of other
+    # clips in between must not disturb them.  8 clips of 4x64x64 and one split keep the BN groups large enough
+    # (>= 128 values) for the run-to-run noise of these gradients to stay ~1e-3; a clobbered statistic is O(1).
+    m, sd = build('S', 5, 1, 'class', torch.float32)
     m.train()
-    m.zero_grad(set_to_none=True)
-    ce(m(x1), y).backward()
-    ref = {k: p.grad.clone() for k, p in m.named_parameters()}
+    x1 = case_clip((8, 3, 4, 64, 64)).float().cuda()
+    x2 = O.det_clip((8, 3, 4, 64, 64), 'clip2', torch.float32).cuda() * 3 + 1
+    y = (torch.arange(8) % 5).view(8, 1).cuda()
+    def clean_run():
+        m.zero_grad(set_to_none=True)
+        ce(m(x1), y).backward()
+        return {k: p.grad.clone() for k, p in m.named_parameters()}
+
+    ref, ref2 = clean_run(), clean_run()
+    noise = max(rel(ref2[k], ref[k]) for k in ref)          # run-to-run noise of two identical passes (atomics order)
     m.zero_grad(set_to_none=True)
     l1 = ce(m(x1), y)
     with torch.no_grad():
         m(x2)
     l1.backward()
-    for k in ('layer1.0.fc1.weight', 'layer1.0.bn2.weight', 'layer3.0.fc2.bias', 'fc2.bias'):
-        assert rel(dict(m.named_parameters())[k].grad, ref[k]) < 1e-3, k
+    errs = {k: rel(p.grad, ref[k]) for k, p in m.named_parameters()}
+    worst = max(errs, key=errs.get)
+    print(f'forward in between: worst gradient deviation {worst} {errs[worst]:.2e}; two identical passes differ by {noise:.2e}')
+    assert errs[worst] <= max(1e-3, 4 * noise), (worst, errs[worst], noise)    # a clobbered statistic is O(1)
 
 
 def _snapshot(m, opt):
@@ -613,3 +634,31 @@ def test_second_device_in_one_process():
         torch.cuda.synchronize(dev)
         outs.append(logits.detach().float().cpu())
     assert rel(outs[1], outs[0]) < 2e-2
+
+
+def test_run_to_run_reproducibility():
+    """Everything that PROPAGATES through the network is reduced in a fixed order (ordered in-CTA reductions; the
+    cross-CTA BN statistics are fp64 sums of fp32 partials, exact -- hence order independent -- unless the partials
+    span more than 2^29 in magnitude), so two identical passes give bit-identical logits and activations gradients.
+    Only the final parameter-gradient sums (fp32 reds of leaf outputs, not amplified by anything) differ in the last
+    bits.  Before the head pooling / head dgrad reductions were ordered, the same comparison gave 3e-6 on the logits
+    and up to 3.5e-2 on deep parameter gradients (that noise times the ~1e4 amplification of 26 train-mode BN layers)."""
+    bad = []
+    for dtype in (torch.bfloat16, torch.float32):
+        m, sd = build('S', 11, 2, 'class', dtype)
+        m.train()
+        x = case_clip((4, 3, 4, 64, 64)).float().cuda()
+        y = torch.tensor([[1], [4], [7], [10]]).cuda()
+        runs = []
+        for _ in range(2):
+            m.zero_grad(set_to_none=True)
+            logits = m(x)
+            torch.nn.functional.cross_entropy(logits, y).backward()
+            runs.append((logits.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()}))
+        noise = {k: rel(runs[1][1][k], runs[0][1][k]) for k in runs[0][1]}
+        worst = max(noise, key=noise.get)
+        print(f'reproducibility [{dtype}]: logits bit-identical {torch.equal(runs[0][0], runs[1][0])}, worst parameter-gradient '
+              f'difference {worst} {noise[worst]:.2e}')
+        if not torch.equal(runs[0][0], runs[1][0]) or noise[worst] >= 1e-4:
+            bad.append((dtype, worst, noise[worst]))
+    assert not bad, bad

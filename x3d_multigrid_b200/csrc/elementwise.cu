@@ -868,13 +868,20 @@ __global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ a, const float* __
 #pragma unroll
     for (int j = 0; j < VEC; ++j) a0[j] += fmaxf(fmaf(x[j], sc[j], sh[j]), 0.f);
   }
-  for (int i = threadIdx.x; i < Cp; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+  // ordered block reduction (no atomics: the pooled features feed fc1/fc2 and, through the loss, every gradient of
+  // the network -- last-bit noise here is amplified ~1e4x by the train-mode BN backward chain):
+  // every thread parks its partial sums in its own slot, then one thread per channel adds the `rows` slots in order.
+  // One CTA per pooled row, so the result is written, not accumulated.
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) atomicAdd(&s_acc[c0 + j], a0[j]);
+  for (int j = 0; j < VEC; ++j) s_acc[(size_t)prow * Cp + c0 + j] = a0[j];
   __syncthreads();
   const float inv = 1.f / (float)P;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&pooled[(int64_t)n * C + i], s_acc[i] * inv);
+  const int nrows = blockDim.x / cv;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    float v = 0.f;
+    for (int r = 0; r < nrows; ++r) v += s_acc[(size_t)r * Cp + i];
+    pooled[(int64_t)n * C + i] = v * inv;
+  }
   (void)a1;
 }
 extern "C" int x3d_bn_relu_pool_fwd(const void* a5, const float* scale, const float* shift, int splits,
@@ -884,12 +891,12 @@ extern "C" int x3d_bn_relu_pool_fwd(const void* a5, const float* scale, const fl
   const int64_t R = pool_t ? N : N * T_;
   const int64_t Pp = pool_t ? T_ * HW : HW;
   if (R * Pp == 0) return 0;
-  cudaError_t e = cudaMemsetAsync(pooled, 0, sizeof(float) * R * C, as_stream(stream));
-  if (e != cudaSuccess) { set_error("memset failed"); return (int)e; }
   X3D_DISPATCH_DTYPE(dt, {
     RowGeom g = make_row_geom<T>(R, Pp, Cp);
-    dim3 grid(g.chunks, (unsigned)R);
-    x3d::launch(bn_relu_pool_fwd_kernel<T>, grid, g.threads, Cp * sizeof(float), as_stream(stream), 
+    g.chunk = Pp;                      // ONE CTA per pooled row: deterministic, no cross-CTA accumulation
+    g.chunks = 1;
+    dim3 grid(1, (unsigned)R);
+    x3d::launch(bn_relu_pool_fwd_kernel<T>, grid, g.threads, (size_t)g.rows * Cp * sizeof(float), as_stream(stream),
         (const T*)a5, scale, shift, splits, pooled, pool_t ? 1 : (int)T_, Pp, (int)C, (int)Cp, g.cv, g.rows, g.chunk);
   });
   X3D_LAUNCH_CHECK();
@@ -1079,29 +1086,44 @@ __global__ void skinny_gemm_kcontig_kernel(const float* __restrict__ A, int64_t 
     }
   }
 }
-// (b) B j-contiguous (sbj == 1): thread = output column, K split over blockIdx.y, fp32 atomics into C
-//     (C zeroed by the launcher unless accumulating; no bias / relu / mul on this path)
+// (b) B j-contiguous (sbj == 1): block = 32 output columns x 8 k-slices; every thread walks its slice of K for its
+//     column (coalesced over the columns), the 8 slices are added in a fixed order through shared memory -- no
+//     atomics: dh / dpooled of the head backward feed the whole backward pass (see bn_relu_pool_fwd_kernel).
 template <int MR>
 __global__ void skinny_gemm_jcontig_kernel(const float* __restrict__ A, int64_t sai, int64_t sak,
                                            const float* __restrict__ B, int64_t sbk, float* __restrict__ C, int64_t ldc,
-                                           int M, int Nn, int K, int kchunk) {
+                                           int M, int Nn, int K, int accumulate) {
   x3d::pdl_prologue();
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= Nn) return;
-  const int k0 = blockIdx.y * kchunk;
+  __shared__ float red[8][MR][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const int j = blockIdx.x * 32 + tx;
+  const int kchunk = (K + 7) / 8;
+  const int k0 = ty * kchunk;
   const int k1 = k0 + kchunk < K ? k0 + kchunk : K;
   float acc[MR];
 #pragma unroll
   for (int i = 0; i < MR; ++i) acc[i] = 0.f;
-  for (int k = k0; k < k1; ++k) {
-    const float b = B[(int64_t)k * sbk + j];
+  if (j < Nn) {
+    for (int k = k0; k < k1; ++k) {
+      const float b = B[(int64_t)k * sbk + j];
 #pragma unroll
-    for (int i = 0; i < MR; ++i)
-      if (i < M) acc[i] = fmaf(__ldg(&A[(int64_t)i * sai + (int64_t)k * sak]), b, acc[i]);
+      for (int i = 0; i < MR; ++i)
+        if (i < M) acc[i] = fmaf(__ldg(&A[(int64_t)i * sai + (int64_t)k * sak]), b, acc[i]);
+    }
   }
 #pragma unroll
-  for (int i = 0; i < MR; ++i)
-    if (i < M && acc[i] != 0.f) atomicAdd(&C[(int64_t)i * ldc + j], acc[i]);
+  for (int i = 0; i < MR; ++i) red[ty][i][tx] = acc[i];
+  __syncthreads();
+  for (int e = threadIdx.x; e < MR * 32; e += 256) {
+    const int i = e >> 5, c = e & 31, jj = blockIdx.x * 32 + c;
+    if (i < M && jj < Nn) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v += red[q][i][c];
+      float* dst = &C[(int64_t)i * ldc + jj];
+      *dst = accumulate ? (*dst + v) : v;
+    }
+  }
 }
 
 extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
@@ -1114,15 +1136,10 @@ extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const fl
       A, sai, sak, B, sbj, C, ldc, (int)M, (int)Nn, (int)K, bias, relu, mul, accumulate)
     if (M <= 8) SK_(8); else if (M <= 16) SK_(16); else SK_(32);
 #undef SK_
-  } else if (M <= 32 && sbj == 1 && !bias && !relu && !mul && ldc == Nn) {
-    if (!accumulate) {
-      cudaError_t e = cudaMemsetAsync(C, 0, sizeof(float) * M * Nn, as_stream(stream));
-      if (e != cudaSuccess) { set_error("x3d_small_gemm: memset failed"); return (int)e; }
-    }
-    const int kchunk = 64;
-    dim3 grid((unsigned)cdiv(Nn, 64), (unsigned)cdiv(K, kchunk));
-#define SJ_(MR) x3d::launch(skinny_gemm_jcontig_kernel<MR>, grid, 64, 0, as_stream(stream),  \
-      A, sai, sak, B, sbk, C, ldc, (int)M, (int)Nn, (int)K, kchunk)
+  } else if (M <= 32 && sbj == 1 && !bias && !relu && !mul) {
+    dim3 grid((unsigned)cdiv(Nn, 32));
+#define SJ_(MR) x3d::launch(skinny_gemm_jcontig_kernel<MR>, grid, 256, 0, as_stream(stream),  \
+      A, sai, sak, B, sbk, C, ldc, (int)M, (int)Nn, (int)K, accumulate)
     if (M <= 8) SJ_(8); else if (M <= 16) SJ_(16); else SJ_(32);
 #undef SJ_
   } else {

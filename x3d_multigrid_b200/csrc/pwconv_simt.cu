@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const T* __restrict__ A, i
   constexpr int VEC = Vec<T>::N;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
-  __shared__ float s_stat[STATS ? MAXS * BN * 2 : 1];
+  // fp64: sums of fp32 values are exact in double (order independent) -> run-to-run reproducible statistics
+  __shared__ double s_stat[STATS ? MAXS * BN * 2 : 1];
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const T* __restrict__ A, i
     const int64_t m_last = (m0 + BM - 1 < M - 1) ? m0 + BM - 1 : M - 1;
     s_count = (int)(m_last / P_out - s_first) + 1;
     if (s_count <= MAXS) {
-      for (int i = tid; i < s_count * BN * 2; i += 256) s_stat[i] = 0.f;
+      for (int i = tid; i < s_count * BN * 2; i += 256) s_stat[i] = 0.0;
     }
     __syncthreads();
   }
@@ -128,13 +129,13 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const T* __restrict__ A, i
       for (int j = 0; j < 4; ++j) {
         const float r = round_to<T>(v[j]);
         if (s_count <= MAXS) {
-          float* sp = &s_stat[((int)(s - s_first) * BN + tx * 4 + j) * 2];
-          atomicAdd(sp, r);
-          atomicAdd(sp + 1, r * r);
+          double* sp = &s_stat[((int)(s - s_first) * BN + tx * 4 + j) * 2];
+          atomicAdd(sp, (double)r);
+          atomicAdd(sp + 1, (double)(r * r));
         } else {
           double* gp = stats + (s * (int64_t)ldc + nc + j) * 2;
           atomicAdd(gp, (double)r);
-          atomicAdd(gp + 1, (double)r * (double)r);
+          atomicAdd(gp + 1, (double)(r * r));
         }
       }
     }
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const T* __restrict__ A, i
     for (int i = tid; i < s_count * BN * 2; i += 256) {
       const int s = i / (BN * 2), rem = i % (BN * 2);
       const int col = n0 + rem / 2;
-      const float v = s_stat[i];
+      const float v = (float)s_stat[i];          // the CTA's partial as an fp32 value: the cross-CTA fp64 sum stays exact
       if (col < Nn && v != 0.f) atomicAdd(&stats[((s_first + s) * (int64_t)ldc + col) * 2 + (rem & 1)], (double)v);
     }
   }
