@@ -43,9 +43,10 @@ def parse():
     ap.add_argument('--bn-splits', type=int, default=None)
     ap.add_argument('--loss', default=None, choices=['ce', 'bce'])
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--ddp', default='graph_nccl', choices=['graph_nccl', 'graph_tail', 'eager'],
-                    help='N > 1: whole step incl. the bucketed NCCL allreduce captured in the CUDA graph (default); '
-                         'captured fwd+bwd followed by one eager allreduce + SGD; or no graph at all')
+    ap.add_argument('--ddp', default='graph_tail', choices=['graph_tail', 'graph_nccl', 'eager'],
+                    help='N > 1: captured fwd+bwd followed by one NCCL allreduce of the flat gradient buffer + the one-kernel SGD '
+                         '(default); whole step incl. the bucketed NCCL allreduces captured in the CUDA graph (measured equal at '
+                         '2 GPUs: 12.88 vs 12.86 ms); or the bucketed allreduce issued eagerly from inside backward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-parity', action='store_true', help='skip the golden-logits check of the benchmarked configuration')
     ap.add_argument('--no-gpu-eager', action='store_true', help='reference arm: skip the informational ATen-on-GPU timing')
@@ -321,6 +322,22 @@ def parity_check(args, torch, X, dev):
             'tolerance': 2e-2 if args.dtype == 'bf16' else 1e-4}
 
 
+def teardown(dist, world, *graph_holders):
+    """NCCL kernels captured in a CUDA graph pin the communicator: drop the graphs first, then leave the group.  The
+    process exits right after; a rank that would block in communicator teardown must not keep the launcher alive."""
+    import gc
+    import torch
+    for h in graph_holders:
+        if isinstance(h, dict):
+            h.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)        # no collective teardown: the other ranks may already be gone (rank 0 prints last)
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -365,6 +382,8 @@ def main():
 
     # ---- data-parallel wiring ------------------------------------------------------------
     ddp_mode = 'single' if world == 1 else (args.ddp if use_graph else 'eager')
+    if ddp_mode == 'eager':
+        use_graph = False
     net, reduce_fn = model, None
     if ddp_mode == 'eager':
         net = DistributedX3D(model, broadcast_from=None)
@@ -511,9 +530,8 @@ def main():
         ms, ms_e2e = float(tt[0]), float(tt[1])
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return teardown(dist, world)
+    reduce_fn = None                      # rank 0 is on its own from here on: no collectives below
 
     # ---------------- roofline: every conv class, dominant one reported -------------------------
     peaks = {}
@@ -579,7 +597,7 @@ def main():
                                                  'pw: M*(K+N)*eb + K*N*eb)',
                     'share_of_step': (d['ms'] / prof_steps) / step_ms,
                     'how': roofline_note, 'tensor_peak_tflops': tc_peak, 'classes': classes}
-    if args.kernel_table:
+    if args.kernel_table and world == 1:
         # two extra (untimed) EAGER steps with EVERY C-ABI call bracketed by events: where the step goes
         L.prof_names, L.prof_records = set(L.fn), []
         eng = model.engine()
@@ -632,8 +650,7 @@ def main():
         'cpu_baseline': cpu, 'final_loss': final_loss, 'parity': parity,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown(dist, world)
 
 
 def run_multigrid(args, torch, dist, model, net, opt, crit_fn, reduce_fn, MG, dev, world, rank, local, L, barrier):
@@ -687,9 +704,7 @@ def run_multigrid(args, torch, dist, model, net, opt, crit_fn, reduce_fn, MG, de
     launches = L.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return teardown(dist, world, trainer.graphs)
     shapes = []
     for (li, B, T, S), r in results.items():
         shapes.append({'long_index': li, 'batch_per_gpu': B, 'frames': T, 'crop': S, 'bn_splits': args.bn_splits * MG.LONG_CYCLE[li],
@@ -706,8 +721,7 @@ def run_multigrid(args, torch, dist, model, net, opt, crit_fn, reduce_fn, MG, de
             'shapes': shapes, 'gpu_launches': int(launches), 'cuda_graph': not args.no_graph, 'clocks': clocks,
             'e2e': None, 'roofline': None, 'cpu_baseline': None}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown(dist, world, trainer.graphs)
 
 
 if __name__ == '__main__':

@@ -75,8 +75,10 @@ def main(rank, world, port, mode, outdir, per_rank=4, local_splits=2, dtype='fp3
            'params': {k: p.detach().cpu() for k, p in m.named_parameters()},
            'stats': {k: v.detach().cpu() for k, v in m.named_buffers() if 'split_bn.running' in k}}
     torch.save(out, os.path.join(outdir, f'{mode}_{rank}.pt'))
-    dist.barrier()
-    dist.destroy_process_group()
+    # CUDA graphs that captured NCCL kernels pin the communicator: leave without a collective teardown
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == '__main__':
