@@ -124,6 +124,15 @@ int x3d_pwconv_wgrad(const void* x, const void* dy, float* dw, int64_t N, int64_
                      int64_t W, int64_t K, int64_t Kp, int64_t Nn, int64_t Np, int stride,
                      x3d_dtype_t dt, x3d_stream_t stream);
 
+/* same with a caller-provided scratch buffer (device memory, 16-byte aligned, not shared with a concurrently running
+ * call): the tensor-core kernel then writes one partial dW tile per M split into it and a second small kernel adds
+ * the partials in a fixed order -- deterministic, and free of the per-element fp32 reds of the plain entry point.
+ * Any size >= 1 MB works (the M split adapts); x3d_pwconv_wgrad_workspace_bytes() is the size that never limits it. */
+int x3d_pwconv_wgrad_ws(const void* x, const void* dy, float* dw, int64_t N, int64_t T, int64_t H, int64_t W,
+                        int64_t K, int64_t Kp, int64_t Nn, int64_t Np, int stride, void* workspace,
+                        size_t workspace_bytes, x3d_dtype_t dt, x3d_stream_t stream);
+size_t x3d_pwconv_wgrad_workspace_bytes(void);
+
 /* ---- SubBatchNorm3d (x3d.py:9-58) -------------------------------------------------------- */
 /* train: per-(split,channel) mean/var from per-sample sums -> scale/shift (+saved mean, rstd),
  * running-stat update of split_bn (momentum, unbiased var) and num_batches_tracked += 1. */

@@ -262,13 +262,25 @@ def test_pwconv_fwd_dgrad_wgrad(case, dtype):
     L().call('x3d_pwconv_wgrad', xn.data_ptr(), dyn.data_ptr(), dw.data_ptr(), N, T, H, W, K, Kp, Nn, Np, s, DT[dtype],
              stream())
     assert rel(dw, w64.grad.reshape(Nn, K)) < TOL[dtype]
+    # two-stage variant (scratch buffer, ordered second stage): same result, bit-identical from run to run, and it
+    # ACCUMULATES into dw like the plain entry point
+    ws = torch.empty(8 << 20, dtype=torch.uint8, device='cuda')
+    dws = []
+    for _ in range(2):
+        d2 = torch.ones(Nn, K, dtype=torch.float32, device='cuda')
+        L().call('x3d_pwconv_wgrad_ws', xn.data_ptr(), dyn.data_ptr(), d2.data_ptr(), N, T, H, W, K, Kp, Nn, Np, s,
+                 ws.data_ptr(), ws.numel(), DT[dtype], stream())
+        dws.append(d2)
+    assert rel(dws[0] - 1.0, w64.grad.reshape(Nn, K)) < 2 * TOL[dtype]
+    if dtype == torch.bfloat16 and s == 1:
+        assert torch.equal(dws[0], dws[1])
     d = {kk: v - paths0[kk] for kk, v in L().path_counts().items()}
     if dtype == torch.bfloat16:      # bf16 storage runs the tcgen05 kernels (fp32 storage is the SIMT parity path)
         assert d['pw_dgrad_tc'] == 2 and d['pw_dgrad_simt'] == 0, d
         assert d['pw_fwd_tc'] == 1 or (s == 2 and K >= 64), d
-        assert d['pw_wgrad_tc'] == 1 or s == 2, d
+        assert d['pw_wgrad_tc'] == 3 or s == 2, d
     else:
-        assert d['pw_fwd_simt'] == 1 and d['pw_wgrad_simt'] == 1, d
+        assert d['pw_fwd_simt'] == 1 and d['pw_wgrad_simt'] == 3, d
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])

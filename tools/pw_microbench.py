@@ -38,6 +38,7 @@ def main():
     a = ap.parse_args()
     L = _lib.lib()
     st = torch.cuda.current_stream().cuda_stream
+    WS = torch.empty(32 << 20, dtype=torch.uint8, device='cuda')      # scratch of the two-stage wgrad reduction
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(
         os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {'hbm_gbs': 6650.0}
     N, T = a.batch, a.frames
@@ -69,8 +70,12 @@ def main():
                 L.call('x3d_pwconv_dgrad', dys[j].data_ptr(), wt.data_ptr(), dxs[j].data_ptr(), N, T, H, H, Kp, Np, 1, 0,
                        1, st)
             else:
-                L.call('x3d_pwconv_wgrad', xs[j].data_ptr(), dys[j].data_ptr(), dw.data_ptr(), N, T, H, H, K, Kp, Nn, Np,
-                       1, 1, st)
+                if os.environ.get('X3D_WG_ATOMIC'):
+                    L.call('x3d_pwconv_wgrad', xs[j].data_ptr(), dys[j].data_ptr(), dw.data_ptr(), N, T, H, H, K, Kp, Nn, Np,
+                           1, 1, st)
+                else:
+                    L.call('x3d_pwconv_wgrad_ws', xs[j].data_ptr(), dys[j].data_ptr(), dw.data_ptr(), N, T, H, H, K, Kp, Nn,
+                           Np, 1, WS.data_ptr(), WS.numel(), 1, st)
 
         row = {'layer': name, 'K': K, 'N': Nn, 'M': M, 'count': cnt}
         for kind in a.only.split(','):

@@ -12,7 +12,7 @@ namespace x3d {
 int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, int64_t Np, int64_t P_out,
                   const int* gather, const int* scatter, double* stats, cudaStream_t stream, bool* handled);
 int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t K, int64_t Kp, int64_t Nn,
-                    int64_t Np, cudaStream_t stream, bool* handled);
+                    int64_t Np, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled);
 }
 
 struct RowMap {
@@ -302,9 +302,9 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ X, 
   }
 }
 
-extern "C" int x3d_pwconv_wgrad(const void* x, const void* dy, float* dw, int64_t N, int64_t T_, int64_t H,
-                                int64_t W, int64_t K, int64_t Kp, int64_t Nn, int64_t Np, int stride,
-                                x3d_dtype_t dt, x3d_stream_t stream) {
+static int pwconv_wgrad_impl(const void* x, const void* dy, float* dw, int64_t N, int64_t T_, int64_t H,
+                             int64_t W, int64_t K, int64_t Kp, int64_t Nn, int64_t Np, int stride, void* workspace,
+                             size_t workspace_bytes, x3d_dtype_t dt, x3d_stream_t stream) {
   X3D_CHECK_ARG(Kp % 8 == 0 && Np % 8 == 0, "Kp, Np must be multiples of 8");
   X3D_CHECK_ARG(stride == 1 || stride == 2, "stride must be 1 or 2");
   RowMap map = make_map(T_, H, W, stride);
@@ -312,7 +312,7 @@ extern "C" int x3d_pwconv_wgrad(const void* x, const void* dy, float* dw, int64_
   if (M == 0) return 0;
   if (dt == X3D_BF16 && stride == 1) {
     bool handled = false;
-    int rc = pwconv_wgrad_tc(x, dy, dw, M, K, Kp, Nn, Np, as_stream(stream), &handled);
+    int rc = pwconv_wgrad_tc(x, dy, dw, M, K, Kp, Nn, Np, workspace, workspace_bytes, as_stream(stream), &handled);
     if (handled) {
       count_path(X3D_PATH_PW_WGRAD_TC);
       return rc;
@@ -338,3 +338,15 @@ extern "C" int x3d_pwconv_wgrad(const void* x, const void* dy, float* dw, int64_
   X3D_LAUNCH_CHECK();
   return 0;
 }
+
+extern "C" int x3d_pwconv_wgrad(const void* x, const void* dy, float* dw, int64_t N, int64_t T_, int64_t H,
+                                int64_t W, int64_t K, int64_t Kp, int64_t Nn, int64_t Np, int stride,
+                                x3d_dtype_t dt, x3d_stream_t stream) {
+  return pwconv_wgrad_impl(x, dy, dw, N, T_, H, W, K, Kp, Nn, Np, stride, nullptr, 0, dt, stream);
+}
+extern "C" int x3d_pwconv_wgrad_ws(const void* x, const void* dy, float* dw, int64_t N, int64_t T_, int64_t H,
+                                   int64_t W, int64_t K, int64_t Kp, int64_t Nn, int64_t Np, int stride,
+                                   void* workspace, size_t workspace_bytes, x3d_dtype_t dt, x3d_stream_t stream) {
+  return pwconv_wgrad_impl(x, dy, dw, N, T_, H, W, K, Kp, Nn, Np, stride, workspace, workspace_bytes, dt, stream);
+}
+extern "C" size_t x3d_pwconv_wgrad_workspace_bytes(void) { return (size_t)32 << 20; }

@@ -525,12 +525,13 @@ struct WgParams {
   int tmem_cols;
   int cpa;           // allow the cp.async loader for operands narrower than 64 columns
   int stages;        // operand ring depth (3..8)
+  int ldp;           // two-stage mode: row pitch (floats) of the partial tiles, = NB * number of k parts
 };
 
 __global__ void __launch_bounds__(NTHREADS)
 pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
                    const __nv_bfloat16* __restrict__ DY, const __nv_bfloat16* __restrict__ X, float* __restrict__ dW,
-                   const WgParams p) {
+                   const WgParams p, float* __restrict__ partial) {
   x3d::pdl_trigger();
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_u32 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -701,16 +702,34 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_const
     const int n = n0 + q * 32 + lane;
     const bool n_ok = n < p.Nn;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* wrow = dW + (int64_t)n * p.K;
-    for (int c0 = 0; c0 < p.NB; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(taddr + c0, r);
-      if (n_ok) {
+    if (partial != nullptr) {
+      // two-stage reduction: this CTA's tile goes to its own slice of the workspace with plain 16-byte stores
+      // ([M split][Np][ldp] fp32); pw_wgrad_reduce_kernel adds the slices in a fixed order afterwards.  (One fp32 red
+      // per element per CTA -- up to 2 M same-address reds per launch -- was 60-70 % of the run time of the stage-3/4
+      // layers, and made the result depend on the arrival order.)
+      float* prow = partial + ((size_t)blockIdx.x * p.Np + n) * p.ldp + k0;
+      const bool st_ok = n < p.Np;
+      for (int c0 = 0; c0 < p.NB; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        if (st_ok) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = k0 + c0 + j;
-          const float v = __uint_as_float(r[j]);
-          if (k < p.K && v != 0.f) atomicAdd(wrow + k, v);
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<uint4*>(prow + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+      }
+    } else {
+      float* wrow = dW + (int64_t)n * p.K;
+      for (int c0 = 0; c0 < p.NB; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        if (n_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = k0 + c0 + j;
+            const float v = __uint_as_float(r[j]);
+            if (k < p.K && v != 0.f) atomicAdd(wrow + k, v);
+          }
         }
       }
     }
@@ -723,12 +742,46 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_const
   }
 }
 
+// second stage: dW[n][k] += sum over the M splits of partial[s][n][k], in a fixed order (deterministic).
+// block = 32 consecutive outputs x 8 slices of the split index; slices are combined through shared memory.
+__global__ void __launch_bounds__(256) pw_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW,
+                                                              int nsplit, int Np, int ldp, int Nn, int K) {
+  x3d::pdl_prologue();
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + tx;                 // output index n*K + k
+  const bool ok = o < Nn * K;
+  const int n = ok ? o / K : 0, k = ok ? o - n * K : 0;
+  const float* src = partial + (size_t)n * ldp + k;
+  const size_t sstride = (size_t)Np * ldp;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (ok) {
+    int s = ty;
+    for (; s + 24 < nsplit; s += 32) {
+      a0 += __ldcg(src + (size_t)s * sstride);
+      a1 += __ldcg(src + (size_t)(s + 8) * sstride);
+      a2 += __ldcg(src + (size_t)(s + 16) * sstride);
+      a3 += __ldcg(src + (size_t)(s + 24) * sstride);
+    }
+    for (; s < nsplit; s += 8) a0 += __ldcg(src + (size_t)s * sstride);
+  }
+  red[ty][tx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ty == 0 && ok) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += red[q][tx];
+    dW[o] += v;
+  }
+}
+
 }  // namespace
 
 namespace x3d {
 // dw[Nn][K] (fp32, += ) from x[M][Kp], dy[M][Np] (bf16, dense rows).  *handled = false -> SIMT path.
+// workspace (optional, fp32, >= 1 MB): two-stage deterministic reduction instead of fp32 reds.
 int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t K, int64_t Kp, int64_t Nn,
-                    int64_t Np, cudaStream_t stream, bool* handled) {
+                    int64_t Np, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled) {
   *handled = false;
   static const bool off = getenv("X3D_PW_SIMT") != nullptr;
   if (off) return 0;
@@ -759,9 +812,20 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
   int64_t msplit = (target + ntiles * kz - 1) / (ntiles * kz);
   const int64_t max_split = (M + 511) / 512;
   if (msplit > max_split) msplit = max_split;
-  // every CTA ends with one fp32 red per element of its dW tile: keep the total under ~2M reds
-  const int64_t red_cap = 2000000 / (Np * Kp) > 1 ? 2000000 / (Np * Kp) : 1;
-  if (msplit > red_cap) msplit = red_cap;
+  p.ldp = p.NB * kz;
+  const size_t slice_bytes = (size_t)Np * p.ldp * sizeof(float);
+  static const bool no_ws = getenv("X3D_WG_ATOMIC") != nullptr;             // A/B switch
+  const bool two_stage = workspace != nullptr && !no_ws && workspace_bytes >= slice_bytes &&
+                         (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
+  if (two_stage) {
+    // one slice of the workspace per M split
+    const int64_t ws_cap = (int64_t)(workspace_bytes / slice_bytes);
+    if (msplit > ws_cap) msplit = ws_cap;
+  } else {
+    // every CTA ends with one fp32 red per element of its dW tile: keep the total under ~2M reds
+    const int64_t red_cap = 2000000 / (Np * Kp) > 1 ? 2000000 / (Np * Kp) : 1;
+    if (msplit > red_cap) msplit = red_cap;
+  }
   if (msplit < 1) msplit = 1;
   int64_t rpc = ((M + msplit - 1) / msplit + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
   msplit = (M + rpc - 1) / rpc;
@@ -776,7 +840,8 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
   dim3 grid((unsigned)msplit, (unsigned)ntiles, (unsigned)kz);
   static const bool no_cpa = getenv("X3D_TC_NOCPA") != nullptr;
   p.cpa = no_cpa ? 0 : 1;
-  x3d::launch(pw_wgrad_tc_kernel, grid, NTHREADS, smem, stream, mapDY, mapX, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, p);
+  x3d::launch(pw_wgrad_tc_kernel, grid, NTHREADS, smem, stream, mapDY, mapX, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, p,
+              two_stage ? (float*)workspace : nullptr);
   *handled = true;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -784,6 +849,17 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
     return (int)e;
   }
   count_launch();
+  if (two_stage) {
+    const int64_t outs = Nn * K;
+    x3d::launch(pw_wgrad_reduce_kernel, dim3((unsigned)((outs + 31) / 32)), 256, 0, stream, (const float*)workspace, dw,
+                (int)msplit, (int)Np, p.ldp, (int)Nn, (int)K);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("pwconv_wgrad_tc: reduce launch failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    count_launch();
+  }
   return 0;
 }
 

@@ -109,6 +109,7 @@ class Engine:
         self.arena_f: Optional[Arena] = None
         self.arena_b: Optional[Arena] = None
         self._side = None
+        self.wg_ws = None           # scratch buffer of the two-stage pointwise weight-gradient reduction
         self.use_side = True        # parallel.DistributedX3D switches it off in eager mode (see there)
         self.grad_hook: Optional[Callable[[int], None]] = None   # called after each bucket's grads are final
 
@@ -143,6 +144,9 @@ class Engine:
             if p.device != device or p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError('all parameters must be contiguous fp32 tensors on the input device')
         self.arena_f, self.arena_b = Arena(device), Arena(device)
+        self.wg_ws = None
+        if device.type == 'cuda' and self.dt == BF16 and not os.environ.get('X3D_WG_ATOMIC'):
+            self.wg_ws = torch.empty(int(self.lib.fn['x3d_pwconv_wgrad_workspace_bytes']()), dtype=torch.uint8, device=device)
         # weight-gradient kernels feed nothing downstream: they run on a side stream, concurrently with the
         # dgrad / BN chain of the main stream (fills the SMs that the small late-stage kernels leave idle)
         self._side = torch.cuda.Stream(device) if (device.type == 'cuda' and not os.environ.get('X3D_NO_SIDE')) else None
@@ -277,6 +281,11 @@ class Engine:
 
     def _wgrad(self, name, tensors, *args):
         """launch a weight-gradient kernel on the side stream once everything enqueued so far has run"""
+        if name == 'x3d_pwconv_wgrad' and self.wg_ws is not None:
+            # two-stage deterministic reduction through the engine's scratch buffer (all weight-gradient kernels of a
+            # pass are serialised on one stream, so one buffer serves them all)
+            name = 'x3d_pwconv_wgrad_ws'
+            args = args[:-1] + (self.wg_ws.data_ptr(), self.wg_ws.numel()) + args[-1:]
         main = torch.cuda.current_stream(self.device)
         if self.side is None:
             self.lib.call(name, *args, main.cuda_stream)
