@@ -375,7 +375,7 @@ def test_config2_bf16_matches_reference_golden():
     against the golden the unmodified reference produced in fp64 (oracle/make_golden.py, case m_config2)."""
     before = _paths()
     m, sd, gold, x, labels, logits, loss = _run_net('m_config2', torch.bfloat16)
-    d = _assert_fast_paths(before, allow_simt_fwd=1, allow_simt_wgrad=4)
+    d = _assert_fast_paths(before, allow_simt_fwd=1, allow_simt_wgrad=1)     # the K = 96 downsample conv of layer4.0
     e = rel(logits, gold['logits'])
     wv, wm = _stat_errors(m, gold)
     top1 = float((logits.argmax(1).cpu() == torch.from_numpy(gold['logits']).argmax(1)).float().mean())

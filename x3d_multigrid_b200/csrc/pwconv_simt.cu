@@ -12,7 +12,8 @@ namespace x3d {
 int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, int64_t Np, int64_t P_out,
                   const int* gather, const int* scatter, double* stats, cudaStream_t stream, bool* handled);
 int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t K, int64_t Kp, int64_t Nn,
-                    int64_t Np, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled);
+                    int64_t Np, const int* gather, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                    bool* handled);
 }
 
 struct RowMap {
@@ -310,9 +311,11 @@ static int pwconv_wgrad_impl(const void* x, const void* dy, float* dw, int64_t N
   RowMap map = make_map(T_, H, W, stride);
   const int64_t M = N * T_ * map.Ho * map.Wo;
   if (M == 0) return 0;
-  if (dt == X3D_BF16 && stride == 1) {
+  if (dt == X3D_BF16) {
     bool handled = false;
-    int rc = pwconv_wgrad_tc(x, dy, dw, M, K, Kp, Nn, Np, workspace, workspace_bytes, as_stream(stream), &handled);
+    const int gather[5] = {stride, (int)H, (int)W, map.Ho, map.Wo};
+    int rc = pwconv_wgrad_tc(x, dy, dw, M, K, Kp, Nn, Np, stride > 1 ? gather : nullptr, workspace, workspace_bytes,
+                             as_stream(stream), &handled);
     if (handled) {
       count_path(X3D_PATH_PW_WGRAD_TC);
       return rc;

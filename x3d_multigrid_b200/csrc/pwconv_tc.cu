@@ -526,6 +526,8 @@ struct WgParams {
   int cpa;           // allow the cp.async loader for operands narrower than 64 columns
   int stages;        // operand ring depth (3..8)
   int ldp;           // two-stage mode: row pitch (floats) of the partial tiles, = NB * number of k parts
+  int gs, gH, gW, gHo, gWo;   // strided (downsample) conv: row m = (nt,ho,wo) of dY pairs with row (nt, gs*ho, gs*wo) of X
+                              // (gathered by the cp.async loader; gs = 1: dense)
 };
 
 __global__ void __launch_bounds__(NTHREADS)
@@ -633,6 +635,16 @@ pw_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_const
           const bool isb = q_src[i] >= (1 << 30);
           const bool ok = q_row[i] < rows;
           const unsigned char* src = (isb ? srcB + (q_src[i] - (1 << 30)) : srcA + q_src[i]);
+          if (isb && p.gs > 1 && ok) {
+            // gathered X row of GEMM row mm (downsample branch, x3d.py:272: stride (1,s,s) on the input positions)
+            const int mm = (int)m + q_row[i];
+            const int hw = p.gHo * p.gWo;
+            const int nt = mm / hw, rem = mm - nt * hw;
+            const int ho = rem / p.gWo, wo = rem - ho * p.gWo;
+            const int64_t srow = ((int64_t)nt * p.gH + ho * p.gs) * p.gW + wo * p.gs;
+            const int cc = ((q_src[i] - (1 << 30)) >> 4) - q_row[i] * cpr_b;       // 16-byte chunk within the row
+            src = xb + (srow * p.Kp + cc * 8) * 2;
+          }
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst0 + q_dst[i]),
                        "l"(ok ? src : srcA), "r"(ok ? 16 : 0)
                        : "memory");
@@ -781,13 +793,23 @@ namespace x3d {
 // dw[Nn][K] (fp32, += ) from x[M][Kp], dy[M][Np] (bf16, dense rows).  *handled = false -> SIMT path.
 // workspace (optional, fp32, >= 1 MB): two-stage deterministic reduction instead of fp32 reds.
 int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t K, int64_t Kp, int64_t Nn,
-                    int64_t Np, void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled) {
+                    int64_t Np, const int* gather /* nullptr | {stride, H, W, Ho, Wo}: X rows gathered */,
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream, bool* handled) {
   *handled = false;
   static const bool off = getenv("X3D_PW_SIMT") != nullptr;
   if (off) return 0;
   if (M < 1 || Kp % 8 || Np % 8 || M >= (1ll << 31)) return 0;
   WgParams p;
   p.M = (int)M; p.K = (int)K; p.Kp = (int)Kp; p.Nn = (int)Nn; p.Np = (int)Np;
+  p.gs = 1; p.gH = p.gW = p.gHo = p.gWo = 0;
+  int64_t x_rows = M;
+  if (gather != nullptr && gather[0] > 1) {
+    static const bool no_cpa_g = getenv("X3D_TC_NOCPA") != nullptr;
+    if (Kp >= 64 || no_cpa_g) return 0;   // the row gather lives in the cp.async loader of narrow operands
+    p.gs = gather[0]; p.gH = gather[1]; p.gW = gather[2]; p.gHo = gather[3]; p.gWo = gather[4];
+    x_rows = (M / ((int64_t)p.gHo * p.gWo)) * p.gH * p.gW;
+    if (x_rows >= (1ll << 31)) return 0;
+  }
   const int kparts = (int)((Kp + 255) / 256);
   p.NB = (int)(((Kp + kparts - 1) / kparts + 15) / 16 * 16);
   if (p.NB > 256) return 0;
@@ -832,7 +854,7 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
   p.rows_per_cta = (int)rpc;
   CUtensorMap mapDY, mapX;
   if (!make_map_2d(&mapDY, dy, M, Np, WG_ROWS)) return 0;
-  if (!make_map_2d(&mapX, x, M, Kp, WG_ROWS)) return 0;
+  if (!make_map_2d(&mapX, x, x_rows, Kp, WG_ROWS)) return 0;
   const size_t smem = 1024 + (size_t)p.stages * (p.a_boxes + p.b_boxes_full) * WG_BOX_BYTES + (2 * WG_MAX_STAGES + 1) * 8 + 16;
   static unsigned long long attr_mask = 0;        // per device (the attribute is a per-device property)
   if (first_use_on_device(&attr_mask))
