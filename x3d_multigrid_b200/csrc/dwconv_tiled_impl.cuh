@@ -27,6 +27,9 @@
 // balance of ~5.7 FMA/B (37 TFMA/s fp32 vs 6.5 TB/s): those layers are bound by the fp32 FMA pipe, which
 // is why the inner loop is FFMA2 and everything else is kept off that pipe.
 #include <cuda.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "dwconv_tiled.h"
@@ -428,7 +431,7 @@ constexpr int tw_big() { return (MODE == M_FWD2) ? 8 : 16; }
 
 // (Ho, Wo): extents of the produced tensor
 template <typename T, int MODE>
-TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW) {
+TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW, bool persistent = false) {
   using M = Map<MODE>;
   TilePlan p;
   p.ok = false;
@@ -437,9 +440,17 @@ TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW) {
   TileGeom& g = p.g;
   g.T = T_; g.Cp = Cp; g.Ho = Ho; g.Wo = Wo;
   const int esz = (int)sizeof(T);
-  // Pick (TH, TW, CC) maximising the fraction of useful lanes (ragged tiles, partial channel chunks)
-  // with a mild penalty for halo re-reads and for small CTAs.
+  // Pick (TH, TW, CC).  Persistent kernels (wgrad) and the stride-2 mappings: maximise the fraction of useful lanes
+  // (ragged tiles, partial channel chunks) with a mild penalty for halo re-reads and for small CTAs.  Stride-1 forward /
+  // dgrad (one CTA per tile): minimise the PADDED work  waves x resident CTAs per SM x tile size  -- ragged tiles, partial
+  // channel chunks and, above all, wave quantisation (448 CTAs of 224 threads on 296 slots run as 2 waves at 76 %).
+  // Fitted to a sweep over all tiles on the X3D-M shapes (tools/dw_tile_sweep.py, profiles/r02_dw_tile_sweep.json): it
+  // picks the measured best tile or one within 2 % of it on every layer; 28^2 x 108: 62 -> 50 us, 14^2 x 216: 37 -> 33 us.
   double best = -1.0;
+  int fTH = 0, fTW = 0, fCC = 0;            // tuning knob: X3D_DW_FORCE="TH,TW,CC" pins the tile (tools/dw_tile_sweep.py)
+  if (const char* f = getenv("X3D_DW_FORCE")) sscanf(f, "%d,%d,%d", &fTH, &fTW, &fCC);
+  const bool wave_model = !persistent && (MODE == M_FWD1 || MODE == M_DG1);
+  double best_cost = 1e300, best_useful = 0.0;
   for (int ci = 0; ci < 3; ++ci) {
     const int CC = kCC[ci];
     const int nchunk = (Cp + CC - 1) / CC;
@@ -450,13 +461,30 @@ TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW) {
       for (int TH = PH; TH <= 8; TH += PH) {
         const int patches = (TH / PH) * (TW / PW);
         const int threads = patches * (CC / 2);
-        if (threads < 96 || threads > MAX_THREADS) continue;
+        if (fTH && (TH != fTH || TW != fTW || CC != fCC)) continue;
+        if ((threads < 96 && !fTH) || threads > MAX_THREADS) continue;
         const int th = (Ho + TH - 1) / TH, tw = (Wo + TW - 1) / TW;
         const int IH = M::in_ext(TH), IW = M::in_ext(TW);
         if (IH > 256 || IW > 256) continue;
         const size_t smem = (size_t)NSTAGE * IH * IW * CC * esz;
         if (smem > 160 * 1024) continue;
         const double useful = (double)Ho * Wo * Cp / ((double)th * TH * tw * TW * nchunk * CC);
+        if (wave_model) {
+          const size_t smem_cta = (size_t)(NSTAGE + 1) * IH * IW * CC * esz + 4 * (size_t)TH * TW * CC * esz + 1024;
+          int per_sm = 2048 / threads;
+          const int by_regs = 65536 / (threads * 128), by_smem = (int)((220 * 1024) / smem_cta);
+          if (per_sm > by_regs) per_sm = by_regs;
+          if (per_sm > by_smem) per_sm = by_smem;
+          if (per_sm < 1) per_sm = 1;
+          const double ctas = (double)th * tw * nchunk * (double)N;
+          const double waves = ceil(ctas / (double)(kNumSMs * per_sm));
+          const double cost = waves * per_sm * (double)(TH * TW * CC);
+          if (cost < best_cost || (cost == best_cost && useful > best_useful)) {
+            best_cost = cost; best_useful = useful; best = useful;
+            g.TH = TH; p.TW = TW; p.CC = CC; p.threads = threads;
+          }
+          continue;
+        }
         const double in_per_out = MODE == M_FWD2 ? 4.0 : MODE == M_DG2 ? 0.25 : 1.0;
         const double halo = (double)IH * IW / ((double)TH * TW * in_per_out);
         const double score = useful / (1.0 + 0.3 * (halo - 1.0)) * (threads >= 192 ? 1.0 : 0.9);
@@ -781,7 +809,7 @@ void launch_wgrad_one(const TilePlan& p, const CUtensorMap& xmap, const CUtensor
 template <typename T, int MODE>
 int run_wgrad_tiled(const void* x, const void* dy, float* dw, int64_t N, int T_, int H, int W, int Ho, int Wo, int C,
                     int Cp, const float* scale, const float* shift, int splits, cudaStream_t stream, bool* handled) {
-  TilePlan p = plan_tiles<T, MODE>(N, T_, Ho, Wo, Cp, 2);
+  TilePlan p = plan_tiles<T, MODE>(N, T_, Ho, Wo, Cp, 2, true);
   if (!p.ok) return 0;
   const size_t esz = sizeof(T);
   const size_t dy_stage_bytes = ((size_t)p.g.TH * p.TW * p.CC * esz + 127) / 128 * 128;
