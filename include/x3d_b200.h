@@ -87,6 +87,29 @@ int x3d_stem_conv_s_wgrad(const float* x_ncdhw, const void* dy, float* dw, int64
                           int64_t T, int64_t H, int64_t W, int64_t Co, int64_t Cop, x3d_dtype_t dt,
                           x3d_stream_t stream);
 
+/* ---- GPU-side input pipeline ---------------------------------------------
+ * Source: decoded uint8 frames [B][T][Hs][Ws][3] (NTHWC, RGB).  Per clip a crop window of S x S pixels at (x1, y1) and
+ * an optional horizontal flip -- the integer-window part of MultiScaleRandomCropMultigrid and RandomHorizontalFlip
+ * (transforms/spatial_transforms.py:472-501, 331-349) -- then ToTensor(norm_value) and Normalize(mean, std)
+ * (:35-119; train_x3d_kinetics_multigrid.py:70-73), computed as ((v / norm_value) - mean[c]) / std[c] with the same
+ * fp32 roundings as the reference, i.e. bit-identical values.  mean_std = {mean R,G,B, std R,G,B} (HOST pointer).
+ * x3d_clip_u8_to_f32 materialises the fp32 NCDHW clip the reference's DataLoader would deliver (drop-in input of
+ * ResNet.forward); the *_u8 stem entry points read the frames directly, so no fp32 clip exists at all. */
+typedef struct {
+  int32_t x1, y1; /* top-left corner of the crop window in the source frame */
+  int32_t flip;   /* != 0: horizontal flip */
+  int32_t reserved;
+} x3d_crop_t;
+int x3d_clip_u8_to_f32(const uint8_t* src, const x3d_crop_t* crops_dev, float* dst, int64_t N, int64_t T,
+                       int64_t Hs, int64_t Ws, int64_t S, const float* mean_std, float norm_value,
+                       x3d_stream_t stream);
+int x3d_stem_conv_s_fwd_u8(const uint8_t* src, const x3d_crop_t* crops_dev, const float* w, void* y, int64_t N,
+                           int64_t T, int64_t Hs, int64_t Ws, int64_t S, const float* mean_std, float norm_value,
+                           int64_t Co, int64_t Cop, x3d_dtype_t dt, x3d_stream_t stream);
+int x3d_stem_conv_s_wgrad_u8(const uint8_t* src, const x3d_crop_t* crops_dev, const void* dy, float* dw, int64_t N,
+                             int64_t T, int64_t Hs, int64_t Ws, int64_t S, const float* mean_std, float norm_value,
+                             int64_t Co, int64_t Cop, x3d_dtype_t dt, x3d_stream_t stream);
+
 /* ---- depthwise conv: conv3x3x3 (x3d.py:87-95,150) and conv1_t 5x1x1 (x3d.py:202-208,318) -
  * kernel (kt,kh,kw) in {(3,3,3),(5,1,1)}, pad k/2, stride (1,s,s).  w_packed: fp32 [taps][Cp].
  * Optional fused input transform relu(x*scale[n%splits][c]+shift[..]) (the preceding

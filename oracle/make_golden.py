@@ -213,11 +213,47 @@ def sampler_golden():
                    'rows': rows}, f)
 
 
+def input_pipeline_golden():
+    """tests/golden/input_pipeline.npz: uint8 frames pushed through the REFERENCE's own spatial transform chain
+    (train_x3d_kinetics_multigrid.py:70-73: MultiScaleRandomCropMultigrid -> RandomHorizontalFlip -> ToTensor(255)
+    -> Normalize(KINETICS_MEAN, KINETICS_STD), transforms/spatial_transforms.py) with the crop scale chosen so that
+    the window already has the target size (PIL's resize is then the identity): the fp32 clips the GPU-side input
+    pipeline must reproduce bit for bit."""
+    sys.path.insert(0, REF)
+    from PIL import Image
+    from transforms import spatial_transforms as ST
+    mean = [110.63666788 / 255, 103.16065604 / 255, 96.29023126 / 255]
+    std = [38.7568578 / 255, 37.88248729 / 255, 40.02898126 / 255]
+    B, T, Hs, Ws, S = 3, 3, 40, 48, 32
+    u = O.det_uniform(B * T * Hs * Ws * 3, 4242)
+    frames = np.clip(np.floor((u * 0.5 + 0.5) * 256), 0, 255).astype(np.uint8).reshape(B, T, Hs, Ws, 3)
+    crop = ST.MultiScaleRandomCropMultigrid([S / min(Hs, Ws)], S)
+    flip = ST.RandomHorizontalFlip()
+    chain = ST.Compose([crop, flip, ST.ToTensor(255), ST.Normalize(mean, std)])
+    params = [(0.31, 0.77, 0.2), (0.0, 1.0, 0.9), (0.999, 0.5, 0.49)]        # (tl_x, tl_y, flip p) per clip
+    clips, table = [], []
+    for b in range(B):
+        crop.size, crop.scale = S, S / min(Hs, Ws)
+        crop.tl_x, crop.tl_y = params[b][0], params[b][1]
+        flip.p = params[b][2]
+        cs = int(min(Hs, Ws) * crop.scale)
+        assert cs == S
+        x1, y1 = int(crop.tl_x * (Ws - cs)), int(crop.tl_y * (Hs - cs))
+        table.append([x1, y1, int(flip.p < 0.5), 0])
+        per_t = [chain(Image.fromarray(frames[b, t])) for t in range(T)]     # [3,S,S] each
+        clips.append(torch.stack(per_t, 1))                                  # [3,T,S,S]
+    clip = torch.stack(clips, 0).numpy()
+    np.savez_compressed(os.path.join(GOLD, 'input_pipeline.npz'), frames=frames, crops=np.array(table, dtype=np.int32),
+                        clip=clip, mean=np.array(mean), std=np.array(std))
+    print('input_pipeline', clip.shape, float(clip.mean()), table)
+
+
 if __name__ == '__main__':
     ref = load_reference()
     os.makedirs(GOLD, exist_ok=True)
     manifests(ref)
     sampler_golden()
+    input_pipeline_golden()
     only = sys.argv[1:] or list(CASES)
     for name in only:
         run_case(ref, name, CASES[name])

@@ -3,5 +3,7 @@ KiyoshiKAWASAKI/X3D-Multigrid, behind the reference's own nn.Module surface."""
 from .x3d import (Bottleneck, ResNet, SubBatchNorm3d, Swish, SwishEfficient, conv1x1x1, conv3x3x3,
                   generate_model, get_blocks, get_inplanes)
 
-__all__ = ['Bottleneck', 'ResNet', 'SubBatchNorm3d', 'Swish', 'SwishEfficient', 'conv1x1x1', 'conv3x3x3',
+from .input_pipeline import UInt8Clips, clip_from_uint8, crop_table
+
+__all__ = ['UInt8Clips', 'clip_from_uint8', 'crop_table', 'Bottleneck', 'ResNet', 'SubBatchNorm3d', 'Swish', 'SwishEfficient', 'conv1x1x1', 'conv3x3x3',
            'generate_model', 'get_blocks', 'get_inplanes']

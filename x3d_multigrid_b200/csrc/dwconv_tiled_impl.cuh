@@ -440,7 +440,7 @@ TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW, bool pers
   TileGeom& g = p.g;
   g.T = T_; g.Cp = Cp; g.Ho = Ho; g.Wo = Wo;
   const int esz = (int)sizeof(T);
-  // Pick (TH, TW, CC).  Persistent kernels (wgrad) and the stride-2 mappings: maximise the fraction of useful lanes
+  // Pick (TH, TW, CC).  The stride-2 forward / dgrad mappings: maximise the fraction of useful lanes
   // (ragged tiles, partial channel chunks) with a mild penalty for halo re-reads and for small CTAs.  Stride-1 forward /
   // dgrad (one CTA per tile): minimise the PADDED work  waves x resident CTAs per SM x tile size  -- ragged tiles, partial
   // channel chunks and, above all, wave quantisation (448 CTAs of 224 threads on 296 slots run as 2 waves at 76 %).
@@ -479,6 +479,20 @@ TilePlan plan_tiles(int64_t N, int T_, int Ho, int Wo, int Cp, int PW, bool pers
           const double ctas = (double)th * tw * nchunk * (double)N;
           const double waves = ceil(ctas / (double)(kNumSMs * per_sm));
           const double cost = waves * per_sm * (double)(TH * TW * CC);
+          if (cost < best_cost || (cost == best_cost && useful > best_useful)) {
+            best_cost = cost; best_useful = useful; best = useful;
+            g.TH = TH; p.TW = TW; p.CC = CC; p.threads = threads;
+          }
+          continue;
+        }
+        if (persistent) {
+          // weight gradient: CTAs walk (sample, tile) units in rounds; padded work = rounds x (tile + per-unit pipeline
+          // restart, ~2000 output-channel elements), same sweep (28^2 x 108 stride 2: 107 -> 72 us)
+          const double units = (double)th * tw * (double)N;
+          double gx = floor((2.0 * kNumSMs) / nchunk);
+          if (gx < 1.0) gx = 1.0;
+          if (gx > units) gx = units;
+          const double cost = ceil(units / gx) * ((double)(TH * TW * CC) + 2000.0);
           if (cost < best_cost || (cost == best_cost && useful > best_useful)) {
             best_cost = cost; best_useful = useful; best = useful;
             g.TH = TH; p.TW = TW; p.CC = CC; p.threads = threads;

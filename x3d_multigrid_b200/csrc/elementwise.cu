@@ -861,7 +861,17 @@ __global__ void bn_relu_pool_fwd_kernel(const T* __restrict__ a, const float* __
     sh[j] = shift[b * Cp + c0 + j];
     a0[j] = 0.f; a1[j] = 0.f;
   }
-  for (int64_t p = p0 + prow; p < p1; p += rows) {
+  int64_t p = p0 + prow;
+  for (; p + 3 * (int64_t)rows < p1; p += 4 * (int64_t)rows) {        // 4 independent 16-byte loads in flight
+    float x[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load_vec<T>(a + ((int64_t)n * P + p + (int64_t)u * rows) * Cp + c0, x[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) a0[j] += fmaxf(fmaf(x[u][j], sc[j], sh[j]), 0.f);
+  }
+  for (; p < p1; p += rows) {
     const int64_t off = ((int64_t)n * P + p) * Cp + c0;
     float x[VEC];
     load_vec<T>(a + off, x);
@@ -895,6 +905,10 @@ extern "C" int x3d_bn_relu_pool_fwd(const void* a5, const float* scale, const fl
     RowGeom g = make_row_geom<T>(R, Pp, Cp);
     g.chunk = Pp;                      // ONE CTA per pooled row: deterministic, no cross-CTA accumulation
     g.chunks = 1;
+    g.rows = 1024 / g.cv;              // as many position rows as a CTA holds (the grid is only R CTAs)
+    if ((int64_t)g.rows > Pp) g.rows = (int)Pp;
+    if (g.rows < 1) g.rows = 1;
+    g.threads = g.cv * g.rows;
     dim3 grid(1, (unsigned)R);
     x3d::launch(bn_relu_pool_fwd_kernel<T>, grid, g.threads, (size_t)g.rows * Cp * sizeof(float), as_stream(stream),
         (const T*)a5, scale, shift, splits, pooled, pool_t ? 1 : (int)T_, Pp, (int)C, (int)Cp, g.cv, g.rows, g.chunk);
@@ -1094,10 +1108,11 @@ __global__ void skinny_gemm_jcontig_kernel(const float* __restrict__ A, int64_t 
                                            const float* __restrict__ B, int64_t sbk, float* __restrict__ C, int64_t ldc,
                                            int M, int Nn, int K, int accumulate) {
   x3d::pdl_prologue();
-  __shared__ float red[8][MR][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  constexpr int SL = MR <= 16 ? 16 : 8;                         // k slices (shared scratch <= 34 KB)
+  __shared__ float red[SL][MR][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x SL
   const int j = blockIdx.x * 32 + tx;
-  const int kchunk = (K + 7) / 8;
+  const int kchunk = (K + SL - 1) / SL;
   const int k0 = ty * kchunk;
   const int k1 = k0 + kchunk < K ? k0 + kchunk : K;
   float acc[MR];
@@ -1114,12 +1129,12 @@ __global__ void skinny_gemm_jcontig_kernel(const float* __restrict__ A, int64_t 
 #pragma unroll
   for (int i = 0; i < MR; ++i) red[ty][i][tx] = acc[i];
   __syncthreads();
-  for (int e = threadIdx.x; e < MR * 32; e += 256) {
+  for (int e = threadIdx.x; e < MR * 32; e += 32 * SL) {
     const int i = e >> 5, c = e & 31, jj = blockIdx.x * 32 + c;
     if (i < M && jj < Nn) {
       float v = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v += red[q][i][c];
+      for (int q = 0; q < SL; ++q) v += red[q][i][c];
       float* dst = &C[(int64_t)i * ldc + jj];
       *dst = accumulate ? (*dst + v) : v;
     }
@@ -1138,7 +1153,7 @@ extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const fl
 #undef SK_
   } else if (M <= 32 && sbj == 1 && !bias && !relu && !mul) {
     dim3 grid((unsigned)cdiv(Nn, 32));
-#define SJ_(MR) x3d::launch(skinny_gemm_jcontig_kernel<MR>, grid, 256, 0, as_stream(stream),  \
+#define SJ_(MR) x3d::launch(skinny_gemm_jcontig_kernel<MR>, grid, (MR <= 16 ? 512 : 256), 0, as_stream(stream),  \
       A, sai, sak, B, sbk, C, ldc, (int)M, (int)Nn, (int)K, accumulate)
     if (M <= 8) SJ_(8); else if (M <= 16) SJ_(16); else SJ_(32);
 #undef SJ_

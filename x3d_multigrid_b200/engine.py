@@ -24,6 +24,7 @@ import torch
 
 from . import _lib
 from ._lib import BF16, F32, PackDesc
+from .input_pipeline import UInt8Clips
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -361,8 +362,15 @@ class Engine:
         C0p = pad8(C0)
         H1, W1 = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
         a_s = self._act(N, T, H1, W1, C0p)
-        lib.call('x3d_stem_conv_s_fwd', _ptr(x), self.p('conv1_s.weight'), _ptr(a_s), N, Ci, T, H, W, C0, C0p,
-                 self.dt, st)
+        if isinstance(x, UInt8Clips):       # decoded frames: crop / flip / ToTensor / Normalize fused into the conv
+            if m.conv1_s.in_channels != 3:
+                raise RuntimeError('uint8 frame input needs a 3-channel stem')
+            lib.call('x3d_stem_conv_s_fwd_u8', _ptr(x.frames), _ptr(x.crops), self.p('conv1_s.weight'), _ptr(a_s), N, T,
+                     x.frames.shape[2], x.frames.shape[3], x.size, x.mean_std_ptr(), float(x.norm_value), C0, C0p,
+                     self.dt, st)
+        else:
+            lib.call('x3d_stem_conv_s_fwd', _ptr(x), self.p('conv1_s.weight'), _ptr(a_s), N, Ci, T, H, W, C0, C0p,
+                     self.dt, st)
         a_t = self._act(N, T, H1, W1, C0p)
         P = T * H1 * W1
         st0 = self._stats(self.arena_f, N, C0p) if training else None
@@ -389,8 +397,13 @@ class Engine:
         da_s = self._act(N, T, H1, W1, C0p)
         lib.call('x3d_dwconv_dgrad', _ptr(da_t), self.pk('conv1_t.d'), _ptr(da_s), N, T, H1, W1, C0p, 5, 1, 1, 1,
                  None, None, None, 1, None, self.dt, st)
-        self._wgrad('x3d_stem_conv_s_wgrad', (x, da_s), _ptr(x), _ptr(da_s), self.g('conv1_s.weight'), N, Ci, T, H, W,
-                    C0, C0p, self.dt)
+        if isinstance(x, UInt8Clips):
+            self._wgrad('x3d_stem_conv_s_wgrad_u8', (x.frames, x.crops, da_s), _ptr(x.frames), _ptr(x.crops), _ptr(da_s),
+                        self.g('conv1_s.weight'), N, T, x.frames.shape[2], x.frames.shape[3], x.size, x.mean_std_ptr(),
+                        float(x.norm_value), C0, C0p, self.dt)
+        else:
+            self._wgrad('x3d_stem_conv_s_wgrad', (x, da_s), _ptr(x), _ptr(da_s), self.g('conv1_s.weight'), N, Ci, T, H, W,
+                        C0, C0p, self.dt)
 
     # ------------------------------------------------------------------ bottleneck
     def block_fwd(self, blk, x, geom, training, save_list):
@@ -654,11 +667,14 @@ class Engine:
     def forward(self, x: torch.Tensor, training: bool, need_grad: bool,
                 dropout_mask: Optional[torch.Tensor] = None):
         """x: [B,3,T,H,W] fp32 NCDHW on CUDA -> logits ([B,C,1] or [B,C,T], fp32), saved state."""
-        if not x.is_cuda:
-            raise RuntimeError('x3d_multigrid_b200 runs on CUDA only (no CPU fallback)')
-        if x.dtype != torch.float32:
-            raise RuntimeError('input clips must be fp32 NCDHW (x3d.py:316)')
-        x = x.contiguous()
+        if isinstance(x, UInt8Clips):
+            pass                              # validated at construction
+        else:
+            if not x.is_cuda:
+                raise RuntimeError('x3d_multigrid_b200 runs on CUDA only (no CPU fallback)')
+            if x.dtype != torch.float32:
+                raise RuntimeError('input clips must be fp32 NCDHW (x3d.py:316) or input_pipeline.UInt8Clips')
+            x = x.contiguous()
         # kernels launch on the CURRENT device: make it the clip's device (a process may drive several GPUs, e.g.
         # the nn.DataParallel replicas the reference supports, x3d.py:278-281 / train_..._multigrid.py:175-177)
         with torch.cuda.device(x.device):

@@ -53,11 +53,13 @@ def _dropout_mask(model, rows, device):
 
 def resnet_forward(model, x, dropout_mask: Optional[torch.Tensor] = None):
     """ResNet.forward (x3d.py:316-345)."""
-    _require_cuda(x, 'ResNet.forward')
-    if x.dim() != 5:
-        raise RuntimeError('expected a [B, C, T, H, W] clip batch')
-    if x.requires_grad:
-        raise NotImplementedError('gradients w.r.t. the input clip are not produced by this path')
+    from .input_pipeline import UInt8Clips
+    if not isinstance(x, UInt8Clips):
+        _require_cuda(x, 'ResNet.forward')
+        if x.dim() != 5:
+            raise RuntimeError('expected a [B, C, T, H, W] clip batch')
+        if x.requires_grad:
+            raise NotImplementedError('gradients w.r.t. the input clip are not produced by this path')
     B, _, T = x.shape[:3]
     rows = B if model.task == 'class' else B * T
     mask = dropout_mask if dropout_mask is not None else _dropout_mask(model, rows, x.device)
