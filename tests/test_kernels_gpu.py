@@ -284,8 +284,10 @@ def test_pwconv_fwd_dgrad_wgrad(case, dtype):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-def test_stem_conv_s(dtype):
-    N, T, H, W, Co = 2, 3, 11, 14, 24
+@pytest.mark.parametrize('hw', [(11, 14), (12, 16), (21, 72), (40, 140)])   # W % 4 == 0: cp.async-pipelined wgrad kernel
+def test_stem_conv_s(dtype, hw):
+    N, T, Co = 2, 3, 24
+    H, W = hw
     x = O.det_clip((N, 3, T, H, W), 'stemx', torch.float32).cuda()
     w = O.det_tensor((Co, 3, 1, 3, 3), 'stemw', scale=0.3, dtype=torch.float32).cuda()
     w64 = w.double().cpu().requires_grad_(True)

@@ -826,9 +826,10 @@ int pwconv_wgrad_tc(const void* x, const void* dy, float* dw, int64_t M, int64_t
   if (target < kNumSMs) target = kNumSMs;
   if (target > 4 * kNumSMs) target = 4 * kNumSMs;
   int per_sm = (int)((target + kNumSMs - 1) / kNumSMs);
-  while (per_sm > 1 && per_sm * 3 * stage_kb > 200) --per_sm;
+  static const int smem_kb = getenv("X3D_WG_SMEM_KB") ? atoi(getenv("X3D_WG_SMEM_KB")) : 200;   // tuning knob
+  while (per_sm > 1 && per_sm * 3 * stage_kb > smem_kb) --per_sm;
   if (target > (int64_t)per_sm * kNumSMs) target = (int64_t)per_sm * kNumSMs;
-  p.stages = (200 / per_sm) / stage_kb;
+  p.stages = (smem_kb / per_sm) / stage_kb;
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
   if (p.stages < 3) p.stages = 3;
   int64_t msplit = (target + ntiles * kz - 1) / (ntiles * kz);

@@ -377,6 +377,167 @@ __global__ void __launch_bounds__(MAXT, MINB) stem_wgrad_reg_kernel(const SRC x,
     }
 }
 
+// ---- wgrad, cp.async-pipelined (fp32 NCDHW clips whose rows are 16-byte aligned: the benchmark shapes) ----------
+// Same role decomposition as stem_wgrad_reg_kernel (warp = input channel x 8 output channels, 72 register accumulators),
+// but the operands of a chunk -- 32 consecutive output positions of one output row: a 3 x 3 x 72-float input patch and
+// 32 dy rows -- are staged through an NST-deep shared-memory ring with 16-byte cp.async (zero fill at the image
+// borders).  In the register version the 9 warps of a CTA share one chunk, so only ~8 KB of distinct bytes were in
+// flight per SM and the kernel ran at a quarter of the HBM rate (0.44 ms for 308 MB); here every CTA keeps NST-1
+// chunks (4 KB each) in flight without holding registers for them.
+constexpr int SP_NST = 6;        // ring depth
+constexpr int SP_XSEG = 72;      // floats per (ci, row) segment: input columns 2*wo0-4 .. 2*wo0+67
+template <typename T>
+__global__ void __launch_bounds__(288, 2) stem_wgrad_pipe_kernel(const float* __restrict__ x, const T* __restrict__ dy,
+                                                                 float* __restrict__ dw, int T_, int H, int W, int Ho,
+                                                                 int Wo, int Co, int Cop, int wblocks, int64_t nchunks,
+                                                                 int64_t chunks_per_cta) {
+  x3d::pdl_prologue();
+  extern __shared__ __align__(16) unsigned char sp_smem[];
+  const int dy_bytes = 32 * Cop * (int)sizeof(T);
+  const int stage_bytes = 9 * SP_XSEG * 4 + dy_bytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ci = warp % 3, cg = warp / 3;
+  const int64_t c_begin = (int64_t)blockIdx.x * chunks_per_cta;
+  int64_t c_end = c_begin + chunks_per_cta;
+  if (c_end > nchunks) c_end = nchunks;
+  const int n_mine = c_end > c_begin ? (int)(c_end - c_begin) : 0;
+  const int64_t HW = (int64_t)H * W;
+  const int n_x16 = 9 * (SP_XSEG / 4), n_d16 = dy_bytes / 16;        // 16-byte copies per chunk (162 + 96 | 192)
+
+  // per-thread copy slots (chunk invariant): slot 0 = copy number tid, slot 1 = tid + 288 (fp32 dy only)
+  int k_seg[2], k_piece[2], k_byte0[2], k_pos[2];
+  int64_t k_xoff[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int q = tid + u * 288;
+    k_seg[u] = -2;                                           // -2: unused, -1: dy copy, >= 0: x segment
+    k_piece[u] = k_byte0[u] = k_pos[u] = 0;
+    k_xoff[u] = 0;
+    if (q < n_x16) {
+      k_seg[u] = q / (SP_XSEG / 4);
+      k_piece[u] = q - k_seg[u] * (SP_XSEG / 4);
+      k_xoff[u] = (int64_t)(k_seg[u] / 3) * T_ * HW;         // channel plane offset
+    } else if (q < n_x16 + n_d16) {
+      k_seg[u] = -1;
+      k_byte0[u] = (q - n_x16) * 16;
+      k_pos[u] = k_byte0[u] / (Cop * (int)sizeof(T));
+    }
+  }
+  // coordinates of the next chunk to be issued, advanced incrementally (no divisions in the loop)
+  int is_wb, is_ho, is_t;
+  int64_t is_n;
+  {
+    const int64_t c = c_begin;
+    is_wb = (int)(c % wblocks);
+    int64_t r = c / wblocks;
+    is_ho = (int)(r % Ho);
+    const int64_t plane = r / Ho;
+    is_n = plane / T_;
+    is_t = (int)(plane - is_n * T_);
+  }
+  auto issue = [&](int i) {                  // stage the next chunk into ring slot i % SP_NST
+    const int wo0 = is_wb * 32, ho = is_ho;
+    const int64_t plane = is_n * T_ + is_t;
+    unsigned char* st = sp_smem + (size_t)(i % SP_NST) * stage_bytes;
+    const float* xplane = x + (is_n * 3 * T_ + is_t) * HW;
+    const unsigned char* dyrow = reinterpret_cast<const unsigned char*>(dy) +
+                                 ((plane * Ho + ho) * (int64_t)Wo + wo0) * Cop * sizeof(T);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (k_seg[u] >= 0) {
+        const int j = k_seg[u] % 3;
+        const int hh = 2 * ho + j - 1;
+        const int col0 = 2 * wo0 - 4 + 4 * k_piece[u];
+        int valid = 0;
+        if (hh >= 0 && hh < H && col0 >= 0) {
+          valid = W - col0;
+          valid = valid > 4 ? 4 : (valid < 0 ? 0 : valid);
+        }
+        const float* src = xplane + k_xoff[u] + (valid ? (int64_t)hh * W + col0 : 0);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(st + (k_seg[u] * SP_XSEG + k_piece[u] * 4) * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(valid * 4) : "memory");
+      } else if (k_seg[u] == -1) {
+        const bool ok = wo0 + k_pos[u] < Wo;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(st + 9 * SP_XSEG * 4 + k_byte0[u]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(dyrow + (ok ? k_byte0[u] : 0)),
+                     "r"(ok ? 16 : 0)
+                     : "memory");
+      }
+    }
+    if (++is_wb == wblocks) {
+      is_wb = 0;
+      if (++is_ho == Ho) {
+        is_ho = 0;
+        if (++is_t == T_) { is_t = 0; ++is_n; }
+      }
+    }
+  };
+
+  float2 acc[9][4];
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int i = 0; i < SP_NST - 1; ++i) {
+    if (i < n_mine) issue(i);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+#pragma unroll 1
+  for (int i = 0; i < n_mine; ++i) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(SP_NST - 2) : "memory");    // this thread's copies of chunk i landed
+    __syncthreads();                                                           // ... everybody's; slot of chunk i-1 is free
+    if (i + SP_NST - 1 < n_mine) issue(i + SP_NST - 1);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    const unsigned char* st = sp_smem + (size_t)(i % SP_NST) * stage_bytes;
+    const float* xs = reinterpret_cast<const float*>(st) + (ci * 3) * SP_XSEG + 3 + 2 * lane;      // col 2*wo-1
+    float xv[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) xv[j * 3 + k] = xs[j * SP_XSEG + k];
+    float d[8];
+    const T* dp = reinterpret_cast<const T*>(st + 9 * SP_XSEG * 4) + lane * Cop + cg * 8;
+    if (sizeof(T) == 2) {
+      load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(dp), d);
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(dp), b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dp) + 4);
+      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+    }
+#pragma unroll
+    for (int ii = 0; ii < 9; ++ii) {
+      const float2 xx = make_float2(xv[ii], xv[ii]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[ii][j] = __ffma2_rn(xx, make_float2(d[2 * j], d[2 * j + 1]), acc[ii][j]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = acc[i][j].x, b = acc[i][j].y;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      acc[i][j] = make_float2(a, b);
+    }
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = i * 8 + 2 * j;
+      if (lane == (e & 31) || lane == ((e + 1) & 31)) {
+        const bool second = lane != (e & 31);
+        const int c = cg * 8 + 2 * j + (second ? 1 : 0);
+        const float v = second ? acc[i][j].y : acc[i][j].x;
+        if (c < Co && v != 0.f) atomicAdd(&dw[(int64_t)c * 27 + ci * 9 + i], v);
+      }
+    }
+}
+
 extern "C" int x3d_stem_conv_s_wgrad(const float* x, const void* dy, float* dw, int64_t N, int64_t Ci, int64_t T_,
                                      int64_t H, int64_t W, int64_t Co, int64_t Cop, x3d_dtype_t dt,
                                      x3d_stream_t stream) {
@@ -387,6 +548,23 @@ extern "C" int x3d_stem_conv_s_wgrad(const float* x, const void* dy, float* dw, 
   if (total == 0) return 0;
   const int roles = (int)(Ci * (Cop / 8));
   static const bool old_kernel = getenv("X3D_STEM_WGRAD_SMEM") != nullptr;      // A/B switch
+  static const bool no_pipe = getenv("X3D_STEM_WGRAD_REG") != nullptr;          // A/B switch
+  if (Ci == 3 && Cop == 24 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && !old_kernel && !no_pipe) {
+    const int wblocks = (int)cdiv(Wo, 32);
+    const int64_t nchunks = N * T_ * Ho * wblocks;
+    int64_t blocks = 2 * kNumSMs;
+    if (blocks > nchunks) blocks = nchunks;
+    const int64_t cpc = cdiv(nchunks, blocks);
+    blocks = cdiv(nchunks, cpc);
+    X3D_DISPATCH_DTYPE(dt, {
+      const size_t smem = (size_t)SP_NST * (9 * SP_XSEG * 4 + 32 * Cop * sizeof(T));
+      x3d::launch(stem_wgrad_pipe_kernel<T>, (unsigned)blocks, 288, smem, as_stream(stream), x, (const T*)dy, dw, (int)T_,
+                  (int)H, (int)W, Ho, Wo, (int)Co, (int)Cop, wblocks, nchunks, cpc);
+    });
+    X3D_LAUNCH_CHECK();
+    return 0;
+  }
   if (roles <= 12 && (int64_t)Ho * Wo < (1ll << 30) && !old_kernel) {
     const int cpp = (int)cdiv((int64_t)Ho * Wo, 32);
     const int64_t planes = N * T_, nchunks = planes * cpp;

@@ -282,6 +282,8 @@ class Engine:
 
     def _wgrad(self, name, tensors, *args):
         """launch a weight-gradient kernel on the side stream once everything enqueued so far has run"""
+        if os.environ.get('X3D_DBG_SKIP_WGRAD'):          # profiling experiment: main chain alone
+            return
         if name == 'x3d_pwconv_wgrad' and self.wg_ws is not None:
             # two-stage deterministic reduction through the engine's scratch buffer (all weight-gradient kernels of a
             # pass are serialised on one stream, so one buffer serves them all)
