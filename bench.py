@@ -280,19 +280,20 @@ def conv_cost(name, a, eb, unpad):
         cls = {'x3d_dwconv_fwd': 'dw_fwd', 'x3d_dwconv_dgrad': 'dw_dgrad', 'x3d_dwconv_wgrad': 'dw_wgrad'}[name]
         return cls, io * C + taps * C * 4, io * Cp + taps * Cp * 4, 2 * N * T * Ho * Wo * C * taps
     # pointwise: x, w, y, N, T, H, W, Kp, Np, stride  |  dy, wT, dx, N, T, H, W, Kp, Np, stride, acc  |  wgrad: ..., K, Kp, Nn, Np, stride
-    if name == 'x3d_pwconv_wgrad':
+    if name in ('x3d_pwconv_wgrad', 'x3d_pwconv_wgrad_ws'):
         N, T, H, W, K, Kp, Nn, Np, s = a[3:12]
     else:
         N, T, H, W, Kp, Np, s = a[3:10]
         K, Nn = unpad.get(Kp, Kp), unpad.get(Np, Np)
     M = N * T * ((H - 1) // s + 1) * ((W - 1) // s + 1)
-    cls = {'x3d_pwconv_fwd': 'pw_fwd', 'x3d_pwconv_dgrad': 'pw_dgrad', 'x3d_pwconv_wgrad': 'pw_wgrad'}[name]
+    cls = {'x3d_pwconv_fwd': 'pw_fwd', 'x3d_pwconv_dgrad': 'pw_dgrad', 'x3d_pwconv_wgrad': 'pw_wgrad',
+           'x3d_pwconv_wgrad_ws': 'pw_wgrad'}[name]
     wbytes = 4 if cls == 'pw_wgrad' else eb
     return cls, M * (K + Nn) * eb + K * Nn * wbytes, M * (Kp + Np) * eb + Kp * Np * wbytes, 2 * M * K * Nn
 
 
 CONV_CALLS = ('x3d_dwconv_fwd', 'x3d_dwconv_dgrad', 'x3d_dwconv_wgrad', 'x3d_pwconv_fwd', 'x3d_pwconv_dgrad',
-              'x3d_pwconv_wgrad')
+              'x3d_pwconv_wgrad', 'x3d_pwconv_wgrad_ws')
 
 
 def parity_check(args, torch, X, dev):

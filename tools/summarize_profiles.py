@@ -9,12 +9,13 @@ import shutil
 import subprocess
 import sys
 
-R = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+R = sys.argv[1] if len(sys.argv) > 1 else 'r02'
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, 'gpurun_out'), os.path.join(ROOT, 'profiles')
 os.makedirs(P, exist_ok=True)
 for name in ('bench.json', 'bench_reference.json', 'kernel_table.json', 'dw_microbench.json', 'pw_microbench.json', 'smi.csv',
-             'multigrid_shapes.jsonl', 'bench_n2.json', 'bench_n4.json', 'bench_n8.json', 'fma_rate.txt', 'bench_xl.json', 'bench_s.json'):
+             'multigrid_shapes.jsonl', 'bench_n2.json', 'bench_n4.json', 'bench_n8.json', 'fma_rate.txt', 'bench_xl.json', 'bench_s.json',
+             'bench_multigrid.json', 'bench_charades.json', 'sass_mnemonics.txt', 'bench_xl_n8.json', 'bench_multigrid_n8.json'):
     src = os.path.join(G, f'{R}_{name}')
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, f'{R}_{name}'))
@@ -40,8 +41,8 @@ if os.path.exists(lc):
     with open(lc, 'rb') as fi, gzip.open(os.path.join(P, f'{R}_launches.csv.gz'), 'wb') as fo:
         shutil.copyfileobj(fi, fo)
 
-# ---- DRAM traffic of the depthwise C-ABI calls: ncu dram counters per launch over eager steps
-tc = os.path.join(G, f'{R}_dw_traffic.csv')
+# ---- DRAM traffic of the conv C-ABI calls: ncu dram counters per launch over one eager step
+tc = os.path.join(G, f'{R}_conv_traffic.csv')
 if os.path.exists(tc):
     import re
     lines = [l for l in open(tc) if not l.startswith('==')]
@@ -52,21 +53,30 @@ if os.path.exists(tc):
         per[row['ID']][row['Metric Name']] = v * scale
         per[row['ID']]['kernel'] = row['Kernel Name']
     calls = collections.defaultdict(list)
+    extra = collections.defaultdict(list)          # second-stage kernels that belong to a call (counted into its bytes)
     for d in per.values():
         k = d['kernel']
         if 'dw3_wgrad' in k:
             calls['x3d_dwconv_wgrad'].append(d)
+        elif 'pw_wgrad_reduce' in k:
+            extra['x3d_pwconv_wgrad'].append(d)
+        elif 'pw_wgrad' in k:
+            calls['x3d_pwconv_wgrad'].append(d)
+        elif 'pw_tc_kernel' in k:
+            calls['x3d_pwconv_fwd' if '<1>' in k or 'true' in k else 'x3d_pwconv_dgrad'].append(d)
         else:
             m = re.search(r'dw3_tiled_kernel<[^,]+, (\d)', k)
             if m:
                 calls['x3d_dwconv_fwd' if int(m.group(1)) < 2 else 'x3d_dwconv_dgrad'].append(d)
-    out = {'how': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:dw3_ on bench.py --no-graph (tiled 3x3x3 '
-                  'kernels; the 5x1x1 stem conv of each call runs the direct kernel and is not in this set)', 'calls': {}}
+    out = {'how': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:dw3_|pw_ on bench.py --no-graph, one eager '
+                  'step (tiled depthwise kernels and tcgen05 GEMMs; the second-stage reduce kernel of the pointwise wgrad is '
+                  'counted into its call)', 'calls': {}}
     for call, ds in calls.items():
         n = len(ds)
-        rd = sum(d.get('dram__bytes_read.sum', 0.0) for d in ds)
-        wr = sum(d.get('dram__bytes_write.sum', 0.0) for d in ds)
-        us = sum(d.get('gpu__time_duration.sum', 0.0) for d in ds)
+        allk = ds + extra.get(call, [])
+        rd = sum(d.get('dram__bytes_read.sum', 0.0) for d in allk)
+        wr = sum(d.get('dram__bytes_write.sum', 0.0) for d in allk)
+        us = sum(d.get('gpu__time_duration.sum', 0.0) for d in allk)
         out['calls'][call] = {'launches': n, 'dram_read_bytes_per_launch': rd / n, 'dram_write_bytes_per_launch': wr / n,
                               'dram_bytes_per_launch': (rd + wr) / n, 'avg_launch_us_under_ncu': us / n}
     with open(os.path.join(P, f'{R}_traffic.json'), 'w') as f:
