@@ -671,3 +671,28 @@ def test_run_to_run_reproducibility():
         if not torch.equal(runs[0][0], runs[1][0]) or noise[worst] >= 1e-4:
             bad.append((dtype, worst, noise[worst]))
     assert not bad, bad
+
+
+def test_multicrop_validation_matches_oracle():
+    """validation path of the reference loop (train_x3d_kinetics_multigrid.py:203-206,240-257; train_x3d_charades.py:
+    156-174): aggregate the split statistics, eval mode, [b, n_crops, ...] clips, softmax-mean / max over the crops"""
+    from x3d_multigrid_b200 import evaluation as EV
+    m, sd = build('S', 11, 2, 'class', torch.float32)
+    x = case_clip((4, 3, 4, 48, 48)).float().cuda()
+    m.train()
+    with torch.no_grad():
+        m(x)                                                   # one training forward: split running statistics move
+    assert EV.prepare_eval(m) == 84 and not m.training
+    fitted = {k: v.detach().double().cpu() if v.is_floating_point() else v.cpu() for k, v in m.state_dict().items()}
+    crops = O.det_clip((2, 3, 3, 4, 48, 48), 'mc', torch.float32).cuda()          # 2 videos x 3 temporal crops
+    with torch.no_grad():
+        want = O.forward(fitted, crops.view(6, 3, 4, 48, 48).double().cpu(), version='S', splits=2, training=False,
+                         conv_impl='aten').view(2, 3, 11, 1)
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 2e-2)):
+        m.set_compute_dtype(dtype)
+        sm, lg = EV.predict_multicrop(m, crops)
+        assert rel(lg, want.mean(1)) < tol and rel(sm, torch.softmax(want, 2).mean(1)) < tol
+        if dtype == torch.float32:
+            assert torch.equal(sm.argmax(1).cpu(), torch.softmax(want, 2).mean(1).argmax(1))
+        pr, mx = EV.predict_multicrop(m, crops, reduce='max')
+        assert rel(mx, want.max(1)[0]) < tol and rel(pr, torch.sigmoid(want).max(1)[0]) < tol

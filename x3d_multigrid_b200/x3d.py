@@ -186,7 +186,12 @@ class ResNet(nn.Module):
         self.base_bn_splits = base_bn_splits
         self.task = task
         if shortcut_type != 'B':
-            raise NotImplementedError("only shortcut_type='B' (the reference scripts' default) is built")
+            # x3d.py:252-261,266-269: the reference's type-'A' shortcut is F.avg_pool3d(x, kernel_size=1, stride=stride)
+            # with an INT stride, i.e. it also halves T while the main branch keeps T (stride (1,s,s)) -- the residual add
+            # raises "size of tensor a must match tensor b at dimension 2" on the first forward of any clip with T > 1
+            # (checked against the reference module).  No script uses it; there is no working behaviour to reproduce.
+            raise NotImplementedError("shortcut_type='A' does not run in the reference either (its shortcut strides T, "
+                                      "x3d.py:253 vs :91); only 'B' (the scripts' default) is built")
         self.in_planes = block_inplanes[0][1]
         self.conv1_s = _StemSpatialConv3d(n_input_channels, self.in_planes, kernel_size=(1, 3, 3), stride=(1, 2, 2),
                                           padding=(0, 1, 1), bias=False)
