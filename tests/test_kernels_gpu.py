@@ -409,7 +409,7 @@ def test_se_swish_forward_backward(dtype, with_se):
     gW1, gb1 = torch.zeros(sw, C, device='cuda'), torch.zeros(sw, device='cuda')
     gW2, gb2 = torch.zeros(C, sw, device='cuda'), torch.zeros(C, device='cuda')
     dg, db = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
-    work = torch.empty(N, Cp, device='cuda')
+    work = torch.empty(N, 2 * Cp + max(sw, 1), device='cuda')
     coef = torch.empty(N, Cp, 3, device='cuda')
     if with_se:
         se_args = (W1.data_ptr(), W2.data_ptr(), pooled.data_ptr(), hidden.data_ptr(), gate.data_ptr(), gW1.data_ptr(),

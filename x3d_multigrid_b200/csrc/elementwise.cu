@@ -660,15 +660,16 @@ extern "C" int x3d_swish_gate_bwd_reduce(const void* dv, const void* a2, const f
   return 0;
 }
 
-// SE backward for one sample (block per sample): produces work[n][c] = dp[n][c]/P and the SE
-// parameter gradients.  u = scale*a2+shift (bn2 output), z = gate*u, dz = dv*swish'(z).
+// SE backward for one sample (block per sample): produces work[n][c] = dp[n][c]/P plus dz2[n][c] and dz1[n][j], the
+// per-sample factors of the SE parameter gradients (summed over the batch, in a fixed order, by se_param_grad_kernel:
+// no atomics -- with the 64-256 clips per GPU of the multigrid shapes, N blocks hammering the same C x w addresses
+// took 38 us per SE block).  u = scale*a2+shift (bn2 output), z = gate*u, dz = dv*swish'(z).
 __global__ void se_bwd_sample_kernel(const double* __restrict__ fwd_stats, const double* __restrict__ bwd_stats,
                                      int splits, double P, int C, int Cp, int sw, const float* __restrict__ scale,
                                      const float* __restrict__ shift, const float* __restrict__ W1,
-                                     const float* __restrict__ W2, const float* __restrict__ pooled,
-                                     const float* __restrict__ hidden, const float* __restrict__ gate,
-                                     float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
-                                     float* __restrict__ db2, float* __restrict__ work) {
+                                     const float* __restrict__ W2, const float* __restrict__ hidden,
+                                     const float* __restrict__ gate, float* __restrict__ work,
+                                     float* __restrict__ dz2_out /*[N][Cp]*/, float* __restrict__ dz1_out /*[N][sw]*/) {
   x3d::pdl_prologue();
   extern __shared__ float sm[];
   float* s_dz2 = sm;           // [C]
@@ -676,13 +677,18 @@ __global__ void se_bwd_sample_kernel(const double* __restrict__ fwd_stats, const
   float* s_h = sm + C + sw;    // [sw]
   const int n = blockIdx.x, b = n % splits;
   for (int j = threadIdx.x; j < sw; j += blockDim.x) s_h[j] = hidden[(int64_t)n * sw + j];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double R1 = bwd_stats[((int64_t)n * Cp + c) * 2 + 0];
-    const double R2 = bwd_stats[((int64_t)n * Cp + c) * 2 + 1];
-    const float g = gate[(int64_t)n * Cp + c];
-    // dgate = sum_thw dz*u = scale*sum(dz*a2) + shift*sum(dz)
-    const float dgate = (float)((double)scale[b * Cp + c] * R2 + (double)shift[b * Cp + c] * R1);
-    s_dz2[c] = dgate * g * (1.f - g);
+  for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+    float dz2 = 0.f;
+    if (c < C) {
+      const double R1 = bwd_stats[((int64_t)n * Cp + c) * 2 + 0];
+      const double R2 = bwd_stats[((int64_t)n * Cp + c) * 2 + 1];
+      const float g = gate[(int64_t)n * Cp + c];
+      // dgate = sum_thw dz*u = scale*sum(dz*a2) + shift*sum(dz)
+      const float dgate = (float)((double)scale[b * Cp + c] * R2 + (double)shift[b * Cp + c] * R1);
+      dz2 = dgate * g * (1.f - g);
+      s_dz2[c] = dz2;
+    }
+    dz2_out[(int64_t)n * Cp + c] = dz2;
   }
   __syncthreads();
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
@@ -694,7 +700,7 @@ __global__ void se_bwd_sample_kernel(const double* __restrict__ fwd_stats, const
     if (lane == 0) {
       float dz1 = s_h[j] > 0.f ? acc : 0.f;
       s_dz1[j] = dz1;
-      atomicAdd(&db1[j], dz1);
+      dz1_out[(int64_t)n * sw + j] = dz1;
     }
   }
   __syncthreads();
@@ -702,17 +708,53 @@ __global__ void se_bwd_sample_kernel(const double* __restrict__ fwd_stats, const
     float dpP = 0.f;
     if (c < C) {
       float dp = 0.f;
-      const float dz2 = s_dz2[c];
-      const float pc = pooled[(int64_t)n * C + c];
-      for (int j = 0; j < sw; ++j) {
-        dp = fmaf(W1[(int64_t)j * C + c], s_dz1[j], dp);
-        atomicAdd(&dW2[(int64_t)c * sw + j], dz2 * s_h[j]);
-        atomicAdd(&dW1[(int64_t)j * C + c], s_dz1[j] * pc);
-      }
-      atomicAdd(&db2[c], dz2);
+      for (int j = 0; j < sw; ++j) dp = fmaf(W1[(int64_t)j * C + c], s_dz1[j], dp);
       dpP = (float)((double)dp / P);
     }
     work[(int64_t)n * Cp + c] = dpP;
+  }
+}
+
+// SE parameter gradients: dW2[c][j] += sum_n dz2[n][c] h[n][j]; dW1[j][c] += sum_n dz1[n][j] p[n][c]; db2, db1.
+// One thread per output element, samples added in order.
+__global__ void se_param_grad_kernel(const float* __restrict__ dz2, const float* __restrict__ dz1,
+                                     const float* __restrict__ pooled, const float* __restrict__ hidden, int N, int C,
+                                     int Cp, int sw, float* __restrict__ dW1, float* __restrict__ db1,
+                                     float* __restrict__ dW2, float* __restrict__ db2) {
+  x3d::pdl_prologue();
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nW = C * sw;
+  if (o < nW) {                                  // dW2[c][j]
+    const int c = o / sw, j = o - c * sw;
+    float a0 = 0.f, a1 = 0.f;
+    int n = 0;
+    for (; n + 1 < N; n += 2) {
+      a0 = fmaf(dz2[(int64_t)n * Cp + c], hidden[(int64_t)n * sw + j], a0);
+      a1 = fmaf(dz2[(int64_t)(n + 1) * Cp + c], hidden[(int64_t)(n + 1) * sw + j], a1);
+    }
+    if (n < N) a0 = fmaf(dz2[(int64_t)n * Cp + c], hidden[(int64_t)n * sw + j], a0);
+    dW2[o] += a0 + a1;
+  } else if (o < 2 * nW) {                       // dW1[j][c]
+    const int q = o - nW;
+    const int j = q / C, c = q - j * C;
+    float a0 = 0.f, a1 = 0.f;
+    int n = 0;
+    for (; n + 1 < N; n += 2) {
+      a0 = fmaf(dz1[(int64_t)n * sw + j], pooled[(int64_t)n * C + c], a0);
+      a1 = fmaf(dz1[(int64_t)(n + 1) * sw + j], pooled[(int64_t)(n + 1) * C + c], a1);
+    }
+    if (n < N) a0 = fmaf(dz1[(int64_t)n * sw + j], pooled[(int64_t)n * C + c], a0);
+    dW1[q] += a0 + a1;
+  } else if (o < 2 * nW + C) {                   // db2[c]
+    const int c = o - 2 * nW;
+    float a = 0.f;
+    for (int n = 0; n < N; ++n) a += dz2[(int64_t)n * Cp + c];
+    db2[c] += a;
+  } else if (o < 2 * nW + C + sw) {              // db1[j]
+    const int j = o - 2 * nW - C;
+    float a = 0.f;
+    for (int n = 0; n < N; ++n) a += dz1[(int64_t)n * sw + j];
+    db1[j] += a;
   }
 }
 
@@ -780,9 +822,14 @@ extern "C" int x3d_se_bn_bwd(const double* fwd_stats, const double* bwd_stats, i
   if (N == 0) return 0;
   if (gate) {
     size_t smem = (C + 2 * sw) * sizeof(float);
+    float* dz2 = work + N * Cp;                 // work: [N][Cp] dp/P | [N][Cp] dz2 | [N][sw] dz1
+    float* dz1 = dz2 + N * Cp;
     x3d::launch(se_bwd_sample_kernel, (unsigned)N, 256, smem, as_stream(stream), fwd_stats, bwd_stats, splits, (double)P, (int)C,
-                                                                       (int)Cp, sw, scale, shift, W1, W2, pooled, hidden,
-                                                                       gate, dW1, db1, dW2, db2, work);
+                (int)Cp, sw, scale, shift, W1, W2, hidden, gate, work, dz2, dz1);
+    X3D_LAUNCH_CHECK();
+    const int64_t outs = 2 * C * sw + C + sw;
+    x3d::launch(se_param_grad_kernel, (unsigned)cdiv(outs, 128), 128, 0, as_stream(stream), (const float*)dz2, (const float*)dz1,
+                pooled, hidden, (int)N, (int)C, (int)Cp, sw, dW1, db1, dW2, db2);
     X3D_LAUNCH_CHECK();
   }
   x3d::launch(se_bn_bwd_coef_kernel, (unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream), fwd_stats, bwd_stats, (int)N, splits,

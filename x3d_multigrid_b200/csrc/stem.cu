@@ -390,7 +390,7 @@ template <typename T>
 __global__ void __launch_bounds__(288, 2) stem_wgrad_pipe_kernel(const float* __restrict__ x, const T* __restrict__ dy,
                                                                  float* __restrict__ dw, int T_, int H, int W, int Ho,
                                                                  int Wo, int Co, int Cop, int wblocks, int64_t nchunks,
-                                                                 int64_t chunks_per_cta) {
+                                                                 int64_t chunks_per_cta, int aligned16) {
   x3d::pdl_prologue();
   extern __shared__ __align__(16) unsigned char sp_smem[];
   const int dy_bytes = 32 * Cop * (int)sizeof(T);
@@ -455,7 +455,16 @@ __global__ void __launch_bounds__(288, 2) stem_wgrad_pipe_kernel(const float* __
         }
         const float* src = xplane + k_xoff[u] + (valid ? (int64_t)hh * W + col0 : 0);
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(st + (k_seg[u] * SP_XSEG + k_piece[u] * 4) * 4);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(valid * 4) : "memory");
+        if (aligned16) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(valid * 4) : "memory");
+        } else {
+          // image rows that are not 16-byte aligned (W = 111, 158 of the multigrid shapes): four 4-byte copies
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst + 4 * e), "l"(src + (e < valid ? e : 0)),
+                         "r"(e < valid ? 4 : 0)
+                         : "memory");
+        }
       } else if (k_seg[u] == -1) {
         const bool ok = wo0 + k_pos[u] < Wo;
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(st + 9 * SP_XSEG * 4 + k_byte0[u]);
@@ -549,8 +558,9 @@ extern "C" int x3d_stem_conv_s_wgrad(const float* x, const void* dy, float* dw, 
   const int roles = (int)(Ci * (Cop / 8));
   static const bool old_kernel = getenv("X3D_STEM_WGRAD_SMEM") != nullptr;      // A/B switch
   static const bool no_pipe = getenv("X3D_STEM_WGRAD_REG") != nullptr;          // A/B switch
-  if (Ci == 3 && Cop == 24 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+  if (Ci == 3 && Cop == 24 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && !old_kernel && !no_pipe) {
+    const int aligned16 = (W % 4 == 0) ? 1 : 0;
     const int wblocks = (int)cdiv(Wo, 32);
     const int64_t nchunks = N * T_ * Ho * wblocks;
     int64_t blocks = 2 * kNumSMs;
@@ -560,7 +570,7 @@ extern "C" int x3d_stem_conv_s_wgrad(const float* x, const void* dy, float* dw, 
     X3D_DISPATCH_DTYPE(dt, {
       const size_t smem = (size_t)SP_NST * (9 * SP_XSEG * 4 + 32 * Cop * sizeof(T));
       x3d::launch(stem_wgrad_pipe_kernel<T>, (unsigned)blocks, 288, smem, as_stream(stream), x, (const T*)dy, dw, (int)T_,
-                  (int)H, (int)W, Ho, Wo, (int)Co, (int)Cop, wblocks, nchunks, cpc);
+                  (int)H, (int)W, Ho, Wo, (int)Co, (int)Cop, wblocks, nchunks, cpc, aligned16);
     });
     X3D_LAUNCH_CHECK();
     return 0;
