@@ -444,6 +444,25 @@ def test_small_gemm_and_sgd():
     L().call('x3d_small_gemm', A.data_ptr(), 1, 70, A.data_ptr(), 70, 1, C2.data_ptr(), 70, 70, 70, 5, None, 0, None, 1,
              stream())
     assert rel(C2, 1 + A.double().t() @ A.double()) < 1e-6
+    # the four head-GEMM flavours at a large-batch (multigrid) size: M = 200 rows is not "skinny" -> tiled kernel
+    R, F1, C5, ncls = 200, 150, 70, 37
+    X = O.det_tensor((R, C5), 'hx', dtype=torch.float32).cuda()
+    W1 = O.det_tensor((F1, C5), 'hw1', dtype=torch.float32).cuda()
+    Dl = O.det_tensor((R, ncls), 'hdl', dtype=torch.float32).cuda()
+    W2 = O.det_tensor((ncls, F1), 'hw2', dtype=torch.float32).cuda()
+    msk = (O.det_tensor((R, F1), 'hm', dtype=torch.float32) > 0).float().cuda() * 2
+    H1 = torch.empty(R, F1, device='cuda')          # NT + relu + dropout mask
+    L().call('x3d_small_gemm', X.data_ptr(), C5, 1, W1.data_ptr(), 1, C5, H1.data_ptr(), F1, R, F1, C5, None, 1,
+             msk.data_ptr(), 0, stream())
+    assert rel(H1, torch.relu(X.double() @ W1.double().t()) * msk.double()) < 1e-6
+    G2 = torch.zeros(ncls, F1, device='cuda')       # TN, accumulate: dW2 = Dl^T H1
+    L().call('x3d_small_gemm', Dl.data_ptr(), 1, ncls, H1.data_ptr(), F1, 1, G2.data_ptr(), F1, ncls, F1, R, None, 0, None, 1,
+             stream())
+    assert rel(G2, Dl.double().t() @ H1.double()) < 1e-6
+    Dh = torch.empty(R, F1, device='cuda')          # NN: dh = Dl W2
+    L().call('x3d_small_gemm', Dl.data_ptr(), ncls, 1, W2.data_ptr(), F1, 1, Dh.data_ptr(), F1, R, F1, ncls, None, 0, None, 0,
+             stream())
+    assert rel(Dh, Dl.double() @ W2.double()) < 1e-6
     # fused SGD == torch.optim.SGD
     from x3d_multigrid_b200._lib import SgdDesc
     p = O.det_tensor((1000,), 'p', dtype=torch.float32).cuda()

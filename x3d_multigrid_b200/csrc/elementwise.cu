@@ -724,37 +724,36 @@ __global__ void se_param_grad_kernel(const float* __restrict__ dz2, const float*
   x3d::pdl_prologue();
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   const int nW = C * sw;
+  // dot product over the samples: 8 independent loads in flight per operand, added in sample order
+  auto dot = [&](const float* __restrict__ a, int64_t sa, const float* __restrict__ b, int64_t sb) {
+    float acc = 0.f;
+    int n = 0;
+    for (; n + 8 <= N; n += 8) {
+      float av[8], bv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        av[u] = __ldg(a + (int64_t)(n + u) * sa);
+        bv[u] = b ? __ldg(b + (int64_t)(n + u) * sb) : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = fmaf(av[u], bv[u], acc);
+    }
+    for (; n < N; ++n) acc = fmaf(__ldg(a + (int64_t)n * sa), b ? __ldg(b + (int64_t)n * sb) : 1.f, acc);
+    return acc;
+  };
   if (o < nW) {                                  // dW2[c][j]
     const int c = o / sw, j = o - c * sw;
-    float a0 = 0.f, a1 = 0.f;
-    int n = 0;
-    for (; n + 1 < N; n += 2) {
-      a0 = fmaf(dz2[(int64_t)n * Cp + c], hidden[(int64_t)n * sw + j], a0);
-      a1 = fmaf(dz2[(int64_t)(n + 1) * Cp + c], hidden[(int64_t)(n + 1) * sw + j], a1);
-    }
-    if (n < N) a0 = fmaf(dz2[(int64_t)n * Cp + c], hidden[(int64_t)n * sw + j], a0);
-    dW2[o] += a0 + a1;
+    dW2[o] += dot(dz2 + c, Cp, hidden + j, sw);
   } else if (o < 2 * nW) {                       // dW1[j][c]
     const int q = o - nW;
     const int j = q / C, c = q - j * C;
-    float a0 = 0.f, a1 = 0.f;
-    int n = 0;
-    for (; n + 1 < N; n += 2) {
-      a0 = fmaf(dz1[(int64_t)n * sw + j], pooled[(int64_t)n * C + c], a0);
-      a1 = fmaf(dz1[(int64_t)(n + 1) * sw + j], pooled[(int64_t)(n + 1) * C + c], a1);
-    }
-    if (n < N) a0 = fmaf(dz1[(int64_t)n * sw + j], pooled[(int64_t)n * C + c], a0);
-    dW1[q] += a0 + a1;
+    dW1[q] += dot(dz1 + j, sw, pooled + c, C);
   } else if (o < 2 * nW + C) {                   // db2[c]
     const int c = o - 2 * nW;
-    float a = 0.f;
-    for (int n = 0; n < N; ++n) a += dz2[(int64_t)n * Cp + c];
-    db2[c] += a;
+    db2[c] += dot(dz2 + c, Cp, nullptr, 0);
   } else if (o < 2 * nW + C + sw) {              // db1[j]
     const int j = o - 2 * nW - C;
-    float a = 0.f;
-    for (int n = 0; n < N; ++n) a += dz1[(int64_t)n * sw + j];
-    db1[j] += a;
+    db1[j] += dot(dz1 + j, sw, nullptr, 0);
   }
 }
 
@@ -1047,49 +1046,65 @@ extern "C" int x3d_bn_relu_pool_bwd_apply(const void* a5, const float* scale, co
 // =======================================================================================
 // small dense fp32 GEMM (head fc1/fc2 and their gradients): 32x32x32 smem tiles
 // =======================================================================================
-__global__ void small_gemm_kernel(const float* __restrict__ A, int64_t sai, int64_t sak, const float* __restrict__ B,
-                                  int64_t sbk, int64_t sbj, float* __restrict__ C, int64_t ldc, int M, int Nn, int K,
-                                  const float* __restrict__ bias, int relu, const float* __restrict__ mul,
-                                  int accumulate) {
+// 64 x 64 x 16 tiles, 256 threads, 4 x 4 outputs per thread; either operand may be k- or row-contiguous (the four head
+// GEMM flavours NT / NN / TN of fc1 / fc2 and their gradients) -- the tile loaders pick the coalesced orientation.
+// No split-K: deterministic.  (The multigrid shapes put 64-256 clips on a GPU, so M = batch is no longer "skinny".)
+__global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict__ A, int64_t sai, int64_t sak,
+                                                         const float* __restrict__ B, int64_t sbk, int64_t sbj,
+                                                         float* __restrict__ C, int64_t ldc, int M, int Nn, int K,
+                                                         const float* __restrict__ bias, int relu,
+                                                         const float* __restrict__ mul, int accumulate) {
   x3d::pdl_prologue();
-  __shared__ float As[32][33];  // [i][k]
-  __shared__ float Bs[32][33];  // [k][j]
-  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < K; k0 += 32) {
-    // A tile: fastest thread index follows the unit-stride dimension
-    for (int r = ty; r < 32; r += 8) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ __align__(16) float As[TK][TM + 4];  // [k][i]
+  __shared__ __align__(16) float Bs[TK][TN + 4];  // [k][j]
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    // 64 x 16 elements per operand = 4 per thread; the fastest thread index follows the unit-stride dimension
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int q = tid + e * 256;
       int i, k;
-      if (sak == 1) { i = r; k = tx; } else { i = tx; k = r; }
-      As[i][k] = (i0 + i < M && k0 + k < K) ? A[(int64_t)(i0 + i) * sai + (int64_t)(k0 + k) * sak] : 0.f;
-    }
-    for (int r = ty; r < 32; r += 8) {
-      int k, j;
-      if (sbj == 1) { k = r; j = tx; } else { k = tx; j = r; }
-      Bs[k][j] = (k0 + k < K && j0 + j < Nn) ? B[(int64_t)(k0 + k) * sbk + (int64_t)(j0 + j) * sbj] : 0.f;
+      if (sak == 1) { k = q % TK; i = q / TK; } else { i = q % TM; k = q / TM; }
+      As[k][i] = (i0 + i < M && k0 + k < K) ? __ldg(&A[(int64_t)(i0 + i) * sai + (int64_t)(k0 + k) * sak]) : 0.f;
+      int j, kb;
+      if (sbk == 1) { kb = q % TK; j = q / TK; } else { j = q % TN; kb = q / TN; }
+      Bs[kb][j] = (j0 + j < Nn && k0 + kb < K) ? __ldg(&B[(int64_t)(k0 + kb) * sbk + (int64_t)(j0 + j) * sbj]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      float bv = Bs[k][tx];
+    for (int k = 0; k < TK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = fmaf(As[ty + 8 * q][k], bv, acc[q]);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
-  const int j = j0 + tx;
-  if (j < Nn) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int i = i0 + ty + 8 * q;
-      if (i < M) {
-        float v = acc[q] + (bias ? bias[j] : 0.f);
-        if (relu) v = fmaxf(v, 0.f);
-        if (mul) v *= mul[(int64_t)i * Nn + j];
-        float* dst = &C[(int64_t)i * ldc + j];
-        *dst = accumulate ? (*dst + v) : v;
-      }
+  for (int i = 0; i < 4; ++i) {
+    const int ii = i0 + ty * 4 + i;
+    if (ii >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int jj = j0 + tx * 4 + j;
+      if (jj >= Nn) continue;
+      float v = acc[i][j] + (bias ? bias[jj] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      if (mul) v *= mul[(int64_t)ii * Nn + jj];
+      float* dst = &C[(int64_t)ii * ldc + jj];
+      *dst = accumulate ? (*dst + v) : v;
     }
   }
 }
@@ -1205,8 +1220,8 @@ extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const fl
     if (M <= 8) SJ_(8); else if (M <= 16) SJ_(16); else SJ_(32);
 #undef SJ_
   } else {
-    dim3 grid((unsigned)cdiv(Nn, 32), (unsigned)cdiv(M, 32)), block(32, 8);
-    x3d::launch(small_gemm_kernel, grid, block, 0, as_stream(stream), A, sai, sak, B, sbk, sbj, C, ldc, (int)M, (int)Nn, (int)K,
+    dim3 grid((unsigned)cdiv(Nn, 64), (unsigned)cdiv(M, 64));
+    x3d::launch(small_gemm_kernel, grid, 256, 0, as_stream(stream), A, sai, sak, B, sbk, sbj, C, ldc, (int)M, (int)Nn, (int)K,
                                                             bias, relu, mul, accumulate);
   }
   X3D_LAUNCH_CHECK();
