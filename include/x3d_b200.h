@@ -211,14 +211,14 @@ int x3d_swish_gate_bwd_reduce(const void* dv, const void* a2, const float* scale
                               int64_t Cp, x3d_dtype_t dt, x3d_stream_t stream);
 /* tiny: SE backward + BN2 backward coefficients.
  * fwd_stats: the dw-conv's per-sample {sum a2, sum a2^2}; bwd_stats: from the reduce above.
- * Produces coef[N][Cp][3] = (E1,E2,E3) with da2 = E1*dz + E2*a2 + E3, accumulates (in sample order, no atomics) the SE
+ * Produces the planar coef[3][N][Cp] = (E1,E2,E3) with da2 = E1*dz + E2*a2 + E3, accumulates (in sample order, no atomics) the SE
  * parameter gradients (NULL pointers: block has no SE) and bn2's dgamma/dbeta. */
 int x3d_se_bn_bwd(const double* fwd_stats, const double* bwd_stats, int64_t N, int splits, int64_t P,
                   int64_t C, int64_t Cp, int sw, const float* gamma, const float* mean,
                   const float* rstd, const float* scale, const float* shift, int train,
                   const float* W1, const float* W2, const float* pooled, const float* hidden,
                   const float* gate, float* dW1, float* db1, float* dW2, float* db2, float* dgamma,
-                  float* dbeta, float* work /*fp32 [N][2*Cp + sw]*/, float* coef /*[N][Cp][3]*/,
+                  float* dbeta, float* work /*fp32 [N][2*Cp + sw]*/, float* coef /*[3][N][Cp]*/,
                   x3d_stream_t stream);
 int x3d_swish_gate_bwd_apply(const void* dv, const void* a2, const float* scale, const float* shift,
                              int splits, const float* gate, const float* coef, void* da2, int64_t N,

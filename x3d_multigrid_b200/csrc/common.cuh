@@ -127,6 +127,18 @@ __device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat16* __restri
   *reinterpret_cast<uint4*>(p) = q;
 }
 
+// VEC (4 or 8) consecutive per-channel constants (scale / shift / coefficients), 16-byte aligned: vector loads --
+// the element-wise kernels read up to six such sets per thread before their loop (48 scalar loads used to be a large
+// part of their run time on the small late-stage tensors)
+template <int VEC>
+__device__ __forceinline__ void load_consts(const float* __restrict__ p, float (&v)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC; i += 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p + i));
+    v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+  }
+}
+
 // value as it will be re-read from storage (so statistics/masks agree with what is stored)
 template <typename T>
 __device__ __forceinline__ float round_to(float x);

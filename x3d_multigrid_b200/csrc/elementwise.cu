@@ -269,12 +269,14 @@ __global__ void bn_act_fwd_kernel(const T* __restrict__ a, const float* __restri
   ROW_PROLOGUE();
   const int b = n % splits;
   float sc[VEC], sh[VEC], rs[VEC], rh[VEC];
+  load_consts<VEC>(scale + b * Cp + c0, sc);
+  load_consts<VEC>(shift + b * Cp + c0, sh);
+  if (RES == 2) {
+    load_consts<VEC>(rscale + b * Cp + c0, rs);
+    load_consts<VEC>(rshift + b * Cp + c0, rh);
+  } else {
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    sc[j] = scale[b * Cp + c0 + j];
-    sh[j] = shift[b * Cp + c0 + j];
-    rs[j] = RES == 2 ? rscale[b * Cp + c0 + j] : 1.f;
-    rh[j] = RES == 2 ? rshift[b * Cp + c0 + j] : 0.f;
+    for (int j = 0; j < VEC; ++j) { rs[j] = 1.f; rh[j] = 0.f; }
   }
   for (int64_t p = p0 + prow; p < p1; p += rows) {
     const int64_t off = ((int64_t)n * P + p) * Cp + c0;
@@ -431,12 +433,9 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restr
   const int b = n % splits;
   const int sC = splits * Cp;
   float A[VEC], B[VEC], Cc[VEC];
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    A[j] = coef[0 * sC + b * Cp + c0 + j];
-    B[j] = coef[1 * sC + b * Cp + c0 + j];
-    Cc[j] = coef[2 * sC + b * Cp + c0 + j];
-  }
+  load_consts<VEC>(coef + 0 * sC + b * Cp + c0, A);
+  load_consts<VEC>(coef + 1 * sC + b * Cp + c0, B);
+  load_consts<VEC>(coef + 2 * sC + b * Cp + c0, Cc);
   for (int64_t p = p0 + prow; p < p1; p += rows) {
     const int64_t off = ((int64_t)n * P + p) * Cp + c0;
     float d[VEC], x[VEC], m[VEC];
@@ -565,11 +564,13 @@ __global__ void swish_gate_fwd_kernel(const T* __restrict__ a2, const float* __r
   ROW_PROLOGUE();
   const int b = n % splits;
   float sc[VEC], sh[VEC];
+  load_consts<VEC>(scale + b * Cp + c0, sc);
+  load_consts<VEC>(shift + b * Cp + c0, sh);
+  if (GATE) {
+    float g[VEC];
+    load_consts<VEC>(gate + (int64_t)n * Cp + c0, g);
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    float g = GATE ? gate[(int64_t)n * Cp + c0 + j] : 1.f;
-    sc[j] = scale[b * Cp + c0 + j] * g;   // z = g*(sc*a+sh)
-    sh[j] = shift[b * Cp + c0 + j] * g;
+    for (int j = 0; j < VEC; ++j) { sc[j] *= g[j]; sh[j] *= g[j]; }   // z = g*(sc*a+sh)
   }
   for (int64_t p = p0 + prow; p < p1; p += rows) {
     const int64_t off = ((int64_t)n * P + p) * Cp + c0;
@@ -619,13 +620,16 @@ __global__ void swish_gate_bwd_reduce_kernel(const T* __restrict__ dv, const T* 
   ROW_PROLOGUE();
   const int b = n % splits;
   float sc[VEC], sh[VEC], a0[VEC], a1[VEC];
+  load_consts<VEC>(scale + b * Cp + c0, sc);
+  load_consts<VEC>(shift + b * Cp + c0, sh);
+  if (GATE) {
+    float g[VEC];
+    load_consts<VEC>(gate + (int64_t)n * Cp + c0, g);
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    float g = GATE ? gate[(int64_t)n * Cp + c0 + j] : 1.f;
-    sc[j] = scale[b * Cp + c0 + j] * g;
-    sh[j] = shift[b * Cp + c0 + j] * g;
-    a0[j] = a1[j] = 0.f;
+    for (int j = 0; j < VEC; ++j) { sc[j] *= g[j]; sh[j] *= g[j]; }
   }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) a0[j] = a1[j] = 0.f;
   for (int64_t p = p0 + prow; p < p1; p += rows) {
     const int64_t off = ((int64_t)n * P + p) * Cp + c0;
     float d[VEC], x[VEC];
@@ -769,10 +773,11 @@ __global__ void se_bn_bwd_coef_kernel(const double* __restrict__ fwd_stats, cons
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= splits * Cp) return;
   const int b = idx / Cp, c = idx % Cp;
+  const int64_t NC = (int64_t)N * Cp;             // coef is planar: [3][N][Cp]
   if (c >= C) {
     for (int n = b; n < N; n += splits) {
-      float* e = coef + ((int64_t)n * Cp + c) * 3;
-      e[0] = e[1] = e[2] = 0.f;
+      const int64_t o = (int64_t)n * Cp + c;
+      coef[o] = 0.f; coef[NC + o] = 0.f; coef[2 * NC + o] = 0.f;
     }
     return;
   }
@@ -803,10 +808,9 @@ __global__ void se_bn_bwd_coef_kernel(const double* __restrict__ fwd_stats, cons
     const int64_t o = (int64_t)n * Cp + c;
     const double g = gate ? (double)gate[o] : 1.0;
     const double dpP = gate ? (double)work[o] : 0.0;
-    float* e = coef + o * 3;
-    e[0] = (float)(A * g);
-    e[1] = (float)B;
-    e[2] = (float)(Cc + A * dpP);
+    coef[o] = (float)(A * g);
+    coef[NC + o] = (float)B;
+    coef[2 * NC + o] = (float)(Cc + A * dpP);
   }
   if (dgamma) atomicAdd(&dgamma[c], (float)sxh);
   if (dbeta) atomicAdd(&dbeta[c], (float)s1);
@@ -847,14 +851,18 @@ __global__ void swish_gate_bwd_apply_kernel(const T* __restrict__ dv, const T* _
   ROW_PROLOGUE();
   const int b = n % splits;
   float sc[VEC], sh[VEC], E1[VEC], E2[VEC], E3[VEC];
+  load_consts<VEC>(scale + b * Cp + c0, sc);
+  load_consts<VEC>(shift + b * Cp + c0, sh);
+  if (GATE) {
+    float g[VEC];
+    load_consts<VEC>(gate + (int64_t)n * Cp + c0, g);
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    float g = GATE ? gate[(int64_t)n * Cp + c0 + j] : 1.f;
-    sc[j] = scale[b * Cp + c0 + j] * g;
-    sh[j] = shift[b * Cp + c0 + j] * g;
-    const float* e = coef + ((int64_t)n * Cp + c0 + j) * 3;
-    E1[j] = e[0]; E2[j] = e[1]; E3[j] = e[2];
+    for (int j = 0; j < VEC; ++j) { sc[j] *= g[j]; sh[j] *= g[j]; }
   }
+  const int64_t NC = (int64_t)gridDim.y * Cp;                 // coef is planar: [3][N][Cp]
+  load_consts<VEC>(coef + 0 * NC + (int64_t)n * Cp + c0, E1);
+  load_consts<VEC>(coef + 1 * NC + (int64_t)n * Cp + c0, E2);
+  load_consts<VEC>(coef + 2 * NC + (int64_t)n * Cp + c0, E3);
   for (int64_t p = p0 + prow; p < p1; p += rows) {
     const int64_t off = ((int64_t)n * P + p) * Cp + c0;
     float d[VEC], x[VEC];

@@ -535,7 +535,7 @@ class Engine:
         bst2 = self._stats(ab, N, Cmp)
         lib.call('x3d_swish_gate_bwd_reduce', _ptr(dv), _ptr(a2), _ptr(bn2.scale), _ptr(bn2.shift), bn2.splits,
                  _ptr(gate), _ptr(bst2), N, P_out, Cmp, dt, st)
-        coef2, work = self._f32(N, Cmp, 3), self._f32(N, 2 * Cmp + max(blk.se_width, 1))
+        coef2, work = self._f32(3, N, Cmp), self._f32(N, 2 * Cmp + max(blk.se_width, 1))
         if blk.has_se:
             se_args = (self.p(pre + '.fc1.weight'), self.p(pre + '.fc2.weight'), _ptr(pooled), _ptr(hidden), _ptr(gate),
                        self.g(pre + '.fc1.weight'), self.g(pre + '.fc1.bias'), self.g(pre + '.fc2.weight'),

@@ -167,7 +167,7 @@ def swish_bwd(x, dy):
     dflat, _ = _flat8(dy.float())
     one = torch.ones(8, device=x.device)
     zero = torch.zeros(8, device=x.device)
-    coef = torch.tensor([1.0, 0.0, 0.0], device=x.device).repeat(8).contiguous()
+    coef = torch.tensor([1.0, 0.0, 0.0], device=x.device).repeat_interleave(8).contiguous()    # planar [3][1][8]
     out = torch.empty_like(flat)
     st = torch.cuda.current_stream(x.device).cuda_stream
     L.call('x3d_swish_gate_bwd_apply', _ptr(dflat), _ptr(flat), _ptr(one), _ptr(zero), 1, None, _ptr(coef), _ptr(out),
