@@ -278,11 +278,7 @@ __global__ void bn_act_fwd_kernel(const T* __restrict__ a, const float* __restri
 #pragma unroll
     for (int j = 0; j < VEC; ++j) { rs[j] = 1.f; rh[j] = 0.f; }
   }
-  for (int64_t p = p0 + prow; p < p1; p += rows) {
-    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
-    float v[VEC], r[VEC];
-    load_vec<T>(a + off, v);
-    if (RES) load_vec<T>(res + off, r);
+  auto body = [&](float (&v)[VEC], const float (&r)[VEC]) {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float y = fmaf(v[j], sc[j], sh[j]);
@@ -291,6 +287,26 @@ __global__ void bn_act_fwd_kernel(const T* __restrict__ a, const float* __restri
       if (RELU) y = fmaxf(y, 0.f);
       v[j] = y;
     }
+  };
+  int64_t p = p0 + prow;
+  for (; p + rows < p1; p += 2 * (int64_t)rows) {               // two rows per iteration: all loads in flight first
+    const int64_t off0 = ((int64_t)n * P + p) * Cp + c0, off1 = off0 + (int64_t)rows * Cp;
+    float v0[VEC], r0[VEC], v1[VEC], r1[VEC];
+    load_vec<T>(a + off0, v0);
+    if (RES) load_vec<T>(res + off0, r0);
+    load_vec<T>(a + off1, v1);
+    if (RES) load_vec<T>(res + off1, r1);
+    body(v0, r0);
+    body(v1, r1);
+    store_vec<T>(out + off0, v0);
+    store_vec<T>(out + off1, v1);
+  }
+  for (; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float v[VEC], r[VEC];
+    load_vec<T>(a + off, v);
+    if (RES) load_vec<T>(res + off, r);
+    body(v, r);
     store_vec<T>(out + off, v);
   }
 }
@@ -333,12 +349,7 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __rest
   float a0[VEC], a1[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) a0[j] = a1[j] = 0.f;
-  for (int64_t p = p0 + prow; p < p1; p += rows) {
-    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
-    float d[VEC], x[VEC], m[VEC];
-    load_vec<T>(dout + off, d);
-    load_vec<T>(a + off, x);
-    if (MASK) load_vec<T>(mask_out + off, m);
+  auto body = [&](float (&d)[VEC], const float (&x)[VEC], const float (&m)[VEC]) {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float dp = (!MASK || m[j] > 0.f) ? d[j] : 0.f;
@@ -346,6 +357,31 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __rest
       a0[j] += dp;
       a1[j] = fmaf(dp, x[j], a1[j]);
     }
+  };
+  int64_t p = p0 + prow;
+  for (; p + rows < p1; p += 2 * (int64_t)rows) {               // two rows per iteration: all loads in flight first
+    const int64_t off0 = ((int64_t)n * P + p) * Cp + c0, off1 = off0 + (int64_t)rows * Cp;
+    float d0[VEC], x0[VEC], m0[VEC], d1[VEC], x1[VEC], m1[VEC];
+    load_vec<T>(dout + off0, d0);
+    load_vec<T>(a + off0, x0);
+    if (MASK) load_vec<T>(mask_out + off0, m0);
+    load_vec<T>(dout + off1, d1);
+    load_vec<T>(a + off1, x1);
+    if (MASK) load_vec<T>(mask_out + off1, m1);
+    body(d0, x0, m0);
+    body(d1, x1, m1);
+    if (STORE) {
+      store_vec<T>(dpre_out + off0, d0);
+      store_vec<T>(dpre_out + off1, d1);
+    }
+  }
+  for (; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float d[VEC], x[VEC], m[VEC];
+    load_vec<T>(dout + off, d);
+    load_vec<T>(a + off, x);
+    if (MASK) load_vec<T>(mask_out + off, m);
+    body(d, x, m);
     if (STORE) store_vec<T>(dpre_out + off, d);
   }
   block_stats_flush<VEC>(a0, a1, cvec, Cp, s_acc, stats + (int64_t)n * Cp * 2);
@@ -436,17 +472,35 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restr
   load_consts<VEC>(coef + 0 * sC + b * Cp + c0, A);
   load_consts<VEC>(coef + 1 * sC + b * Cp + c0, B);
   load_consts<VEC>(coef + 2 * sC + b * Cp + c0, Cc);
-  for (int64_t p = p0 + prow; p < p1; p += rows) {
-    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
-    float d[VEC], x[VEC], m[VEC];
-    load_vec<T>(dout + off, d);
-    load_vec<T>(a + off, x);
-    if (MASK) load_vec<T>(mask_out + off, m);
+  auto body = [&](float (&d)[VEC], const float (&x)[VEC], const float (&m)[VEC]) {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float dp = (!MASK || m[j] > 0.f) ? d[j] : 0.f;
       d[j] = fmaf(A[j], dp, fmaf(B[j], x[j], Cc[j]));
     }
+  };
+  int64_t p = p0 + prow;
+  for (; p + rows < p1; p += 2 * (int64_t)rows) {               // two rows per iteration: all loads in flight first
+    const int64_t off0 = ((int64_t)n * P + p) * Cp + c0, off1 = off0 + (int64_t)rows * Cp;
+    float d0[VEC], x0[VEC], m0[VEC], d1[VEC], x1[VEC], m1[VEC];
+    load_vec<T>(dout + off0, d0);
+    load_vec<T>(a + off0, x0);
+    if (MASK) load_vec<T>(mask_out + off0, m0);
+    load_vec<T>(dout + off1, d1);
+    load_vec<T>(a + off1, x1);
+    if (MASK) load_vec<T>(mask_out + off1, m1);
+    body(d0, x0, m0);
+    body(d1, x1, m1);
+    store_vec<T>(da + off0, d0);
+    store_vec<T>(da + off1, d1);
+  }
+  for (; p < p1; p += rows) {
+    const int64_t off = ((int64_t)n * P + p) * Cp + c0;
+    float d[VEC], x[VEC], m[VEC];
+    load_vec<T>(dout + off, d);
+    load_vec<T>(a + off, x);
+    if (MASK) load_vec<T>(mask_out + off, m);
+    body(d, x, m);
     store_vec<T>(da + off, d);
   }
 }
@@ -556,6 +610,16 @@ extern "C" int x3d_se_fwd(const double* stats, const float* scale, const float* 
 // =======================================================================================
 // Swish (+ SE gate) forward / backward
 // =======================================================================================
+// sigmoid for bf16-storage tensors: one MUFU (tanh.approx, rel. error 2^-11, four times finer than the bf16 the result
+// is stored in) instead of ex2 + rcp; fp32 storage keeps the exact-ish exp / divide path (parity mode)
+template <typename T>
+__device__ __forceinline__ float sigmoid_t(float x) { return sigmoidf_(x); }
+template <>
+__device__ __forceinline__ float sigmoid_t<__nv_bfloat16>(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
 template <typename T, bool GATE>
 __global__ void swish_gate_fwd_kernel(const T* __restrict__ a2, const float* __restrict__ scale,
                                       const float* __restrict__ shift, int splits, const float* __restrict__ gate,
@@ -572,14 +636,29 @@ __global__ void swish_gate_fwd_kernel(const T* __restrict__ a2, const float* __r
 #pragma unroll
     for (int j = 0; j < VEC; ++j) { sc[j] *= g[j]; sh[j] *= g[j]; }   // z = g*(sc*a+sh)
   }
-  for (int64_t p = p0 + prow; p < p1; p += rows) {
+  int64_t p = p0 + prow;
+  for (; p + rows < p1; p += 2 * (int64_t)rows) {               // two rows per iteration: both loads in flight first
+    const int64_t off0 = ((int64_t)n * P + p) * Cp + c0, off1 = off0 + (int64_t)rows * Cp;
+    float x0[VEC], x1[VEC];
+    load_vec<T>(a2 + off0, x0);
+    load_vec<T>(a2 + off1, x1);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float z0 = fmaf(x0[j], sc[j], sh[j]), z1 = fmaf(x1[j], sc[j], sh[j]);
+      x0[j] = z0 * sigmoid_t<T>(z0);
+      x1[j] = z1 * sigmoid_t<T>(z1);
+    }
+    store_vec<T>(v + off0, x0);
+    store_vec<T>(v + off1, x1);
+  }
+  for (; p < p1; p += rows) {
     const int64_t off = ((int64_t)n * P + p) * Cp + c0;
     float x[VEC];
     load_vec<T>(a2 + off, x);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float z = fmaf(x[j], sc[j], sh[j]);
-      x[j] = z * sigmoidf_(z);
+      x[j] = z * sigmoid_t<T>(z);
     }
     store_vec<T>(v + off, x);
   }
@@ -605,8 +684,9 @@ extern "C" int x3d_swish_gate_fwd(const void* a2, const float* scale, const floa
 }
 
 // d swish(z)/dz = s*(1 + z*(1-s)), s = sigmoid(z)   (x3d.py:81-84)
+template <typename T>
 __device__ __forceinline__ float swish_grad(float z) {
-  float s = sigmoidf_(z);
+  float s = sigmoid_t<T>(z);
   return s * fmaf(z, 1.f - s, 1.f);
 }
 
@@ -630,14 +710,32 @@ __global__ void swish_gate_bwd_reduce_kernel(const T* __restrict__ dv, const T* 
   }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) a0[j] = a1[j] = 0.f;
-  for (int64_t p = p0 + prow; p < p1; p += rows) {
+  int64_t p = p0 + prow;
+  for (; p + rows < p1; p += 2 * (int64_t)rows) {               // two rows per iteration: four loads in flight first
+    const int64_t off0 = ((int64_t)n * P + p) * Cp + c0, off1 = off0 + (int64_t)rows * Cp;
+    float d0[VEC], x0[VEC], d1[VEC], x1[VEC];
+    load_vec<T>(dv + off0, d0);
+    load_vec<T>(a2 + off0, x0);
+    load_vec<T>(dv + off1, d1);
+    load_vec<T>(a2 + off1, x1);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float dz0 = d0[j] * swish_grad<T>(fmaf(x0[j], sc[j], sh[j]));
+      const float dz1 = d1[j] * swish_grad<T>(fmaf(x1[j], sc[j], sh[j]));
+      a0[j] += dz0;
+      a1[j] = fmaf(dz0, x0[j], a1[j]);
+      a0[j] += dz1;
+      a1[j] = fmaf(dz1, x1[j], a1[j]);
+    }
+  }
+  for (; p < p1; p += rows) {
     const int64_t off = ((int64_t)n * P + p) * Cp + c0;
     float d[VEC], x[VEC];
     load_vec<T>(dv + off, d);
     load_vec<T>(a2 + off, x);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      float dz = d[j] * swish_grad(fmaf(x[j], sc[j], sh[j]));
+      float dz = d[j] * swish_grad<T>(fmaf(x[j], sc[j], sh[j]));
       a0[j] += dz;
       a1[j] = fmaf(dz, x[j], a1[j]);
     }
@@ -863,14 +961,32 @@ __global__ void swish_gate_bwd_apply_kernel(const T* __restrict__ dv, const T* _
   load_consts<VEC>(coef + 0 * NC + (int64_t)n * Cp + c0, E1);
   load_consts<VEC>(coef + 1 * NC + (int64_t)n * Cp + c0, E2);
   load_consts<VEC>(coef + 2 * NC + (int64_t)n * Cp + c0, E3);
-  for (int64_t p = p0 + prow; p < p1; p += rows) {
+  int64_t p = p0 + prow;
+  for (; p + rows < p1; p += 2 * (int64_t)rows) {               // two rows per iteration: four loads in flight first
+    const int64_t off0 = ((int64_t)n * P + p) * Cp + c0, off1 = off0 + (int64_t)rows * Cp;
+    float d0[VEC], x0[VEC], d1[VEC], x1[VEC];
+    load_vec<T>(dv + off0, d0);
+    load_vec<T>(a2 + off0, x0);
+    load_vec<T>(dv + off1, d1);
+    load_vec<T>(a2 + off1, x1);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float dz0 = d0[j] * swish_grad<T>(fmaf(x0[j], sc[j], sh[j]));
+      const float dz1 = d1[j] * swish_grad<T>(fmaf(x1[j], sc[j], sh[j]));
+      d0[j] = fmaf(E1[j], dz0, fmaf(E2[j], x0[j], E3[j]));
+      d1[j] = fmaf(E1[j], dz1, fmaf(E2[j], x1[j], E3[j]));
+    }
+    store_vec<T>(da2 + off0, d0);
+    store_vec<T>(da2 + off1, d1);
+  }
+  for (; p < p1; p += rows) {
     const int64_t off = ((int64_t)n * P + p) * Cp + c0;
     float d[VEC], x[VEC];
     load_vec<T>(dv + off, d);
     load_vec<T>(a2 + off, x);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      float dz = d[j] * swish_grad(fmaf(x[j], sc[j], sh[j]));
+      float dz = d[j] * swish_grad<T>(fmaf(x[j], sc[j], sh[j]));
       d[j] = fmaf(E1[j], dz, fmaf(E2[j], x[j], E3[j]));
     }
     store_vec<T>(da2 + off, d);
