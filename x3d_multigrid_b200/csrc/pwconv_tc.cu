@@ -151,7 +151,8 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)BN * BK * 2;
   unsigned char* a_s = base;
   unsigned char* b_s = base + S * a_bytes;
-  __nv_bfloat16* c_s = reinterpret_cast<__nv_bfloat16*>(b_s + S * b_bytes);            // [128][cpitch] staging
+  // (cp.async path: the weights are resident in ONE B slot, the ring holds A tiles only)
+  __nv_bfloat16* c_s = reinterpret_cast<__nv_bfloat16*>(b_s + (p.cpa ? 1 : S) * b_bytes);   // [128][cpitch] staging
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(c_s + BM * p.cpitch);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* accum_full = empty_bar + S;
@@ -221,7 +222,9 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         tma_load_2d(b_s, &mapB, accum_empty + 2, 0, n0);
       }
       const unsigned char* Ab = reinterpret_cast<const unsigned char*>(A);
-      int it = 0, prev_s = 0;
+      // D = S-1 tiles of look-ahead: tile `it` is published (full barrier) once D younger copy groups are in flight
+      const int D = S - 1;
+      int it = 0;
       for (int tm = tile_begin; tm < tile_end; ++tm, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
@@ -262,17 +265,23 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           }
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
-        if (it > 0) {                                            // publish the PREVIOUS tile (its copies are done)
-          asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        if (it >= D) {                                           // publish tile it - D (its copies are done)
+          switch (D) {
+            case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
+            case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
+            case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
+            case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
+            default: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
+          }
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[prev_s])) : "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[(it - D) % S])) : "memory");
         }
-        prev_s = s;
       }
       if (it > 0) {
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[prev_s])) : "memory");
+        for (int j = (it > D ? it - D : 0); j < it; ++j)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[j % S])) : "memory");
       }
     } else if (lane == 0) {
       // ===== TMA producer =====
@@ -931,17 +940,20 @@ int pwconv_fwd_tc(const void* x, const void* w, void* y, int64_t M, int64_t Kp, 
     p.accum = scatter[5];                 // dense rows, C += (identity-residual gradient already in dx)
   }
   p.stages = BN > 128 ? 3 : 2;      // small-N layers: 2 stages so that 2-3 CTAs fit per SM (nk is 1-2 there)
+  static const int st_env = getenv("X3D_TC_STAGES") ? atoi(getenv("X3D_TC_STAGES")) : 0;      // tuning knob
+  if (st_env >= 2 && st_env <= 6) p.stages = st_env;
   CUtensorMap mapA, mapB;
   if (!make_map_2d(&mapA, x, M, Kp, BM)) return 0;
   if (!make_map_2d(&mapB, w, Np, Kp, BN)) return 0;
-  const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + (size_t)BN * BK * 2) + (size_t)BM * p.cpitch * 2 +
-                      (2 * p.stages + 6) * 8 + 16 + (size_t)2 * BN * 2 * sizeof(float) + 4096 + 16 + 1024;
+  const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2) + (size_t)(p.cpa ? 1 : p.stages) * ((size_t)BN * BK * 2) +
+                      (size_t)BM * p.cpitch * 2 + (2 * p.stages + 6) * 8 + 16 + (size_t)2 * BN * 2 * sizeof(float) + 4096 +
+                      16 + 1024;
   // resident CTAs: TMEM (512 columns per SM) and shared memory (227 KB per SM) bound the co-residency
   int per_sm = 512 / p.tmem_cols;
   const int by_smem = (int)((227 * 1024) / (smem + 1024));
   if (per_sm > by_smem) per_sm = by_smem;
   if (per_sm < 1) per_sm = 1;
-  static const int per_sm_cap = getenv("X3D_TC_PERSM") ? atoi(getenv("X3D_TC_PERSM")) : 3;
+  static const int per_sm_cap = getenv("X3D_TC_PERSM") ? atoi(getenv("X3D_TC_PERSM")) : 4;
   if (per_sm > per_sm_cap) per_sm = per_sm_cap;
   const int parts_n = (int)((Np + BN - 1) / BN);
   int gx = (kNumSMs * per_sm) / parts_n;
