@@ -426,6 +426,7 @@ def main():
         return loss
 
     ddp_note = ddp_mode
+    reduce_fn_keep = reduce_fn
     if use_graph:
         try:
             graphed = GraphedTrainStep(net, opt, crit_fn, dev_x[0], dev_y[0], reduce_fn=reduce_fn)
@@ -439,6 +440,7 @@ def main():
             model.engine().use_side = True
             net = model
             reduce_fn = lambda flat: dist.all_reduce(flat)
+            reduce_fn_keep = reduce_fn
             graphed = GraphedTrainStep(net, opt, crit_fn, dev_x[0], dev_y[0], reduce_fn=reduce_fn)
         train_step = lambda x, y: graphed(x, y)
     else:
@@ -525,10 +527,59 @@ def main():
     barrier()
     ms_e2e = t0.elapsed_time(t1)
 
+    # ---------------- end-to-end arm with the GPU-side input pipeline: pinned uint8 frames -> H2D -> fused stem ------
+    # (decoded 256 x 256 frames, per-clip crop window + flip; crop / flip / ToTensor / Normalize run on the device)
+    ms_u8, h2d_u8 = None, None
+    if use_graph and args.config in ('train', 'charades') and S <= 256:
+        Hs = 256
+        hu = [torch.randint(0, 256, (B, T, Hs, Hs, 3), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(n_host)]
+        hc = [torch.stack([torch.randint(0, Hs - S + 1, (B,), generator=gen), torch.randint(0, Hs - S + 1, (B,), generator=gen),
+                           torch.randint(0, 2, (B,), generator=gen), torch.zeros(B, dtype=torch.int64)], 1).int().pin_memory()
+              for _ in range(n_host)]
+        ex = X.UInt8Clips(hu[0].to(dev), hc[0].to(dev), S)
+        g8 = GraphedTrainStep(net, opt, crit_fn, ex, dev_y[0], reduce_fn=reduce_fn_keep)
+        st8 = [X.UInt8Clips(torch.empty_like(ex.frames), torch.empty_like(ex.crops), S) for _ in range(2)]
+
+        def prefetch8(i):
+            sl = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[sl])
+                st8[sl].frames.copy_(hu[i % n_host], non_blocking=True)
+                st8[sl].crops.copy_(hc[i % n_host], non_blocking=True)
+                stage_y[sl].copy_(host_y[i % n_host], non_blocking=True)
+                ready[sl].record(copy_stream)
+
+        def loop8(n):
+            for sl in range(2):
+                freed[sl].record()
+            prefetch8(0)
+            tot = 0.0
+            for i in range(n):
+                if i + 1 < n:
+                    prefetch8(i + 1)
+                sl = i % 2
+                torch.cuda.current_stream().wait_event(ready[sl])
+                ls = g8(st8[sl], stage_y[sl])
+                freed[sl].record()
+                tot += float(ls.item())
+            return tot
+
+        loop8(2)
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        loop8(args.steps)
+        u1.record()
+        barrier()
+        ms_u8 = u0.elapsed_time(u1)
+        h2d_u8 = hu[0].numel() + hc[0].numel() * 4 + host_y[0].numel() * host_y[0].element_size()
+
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        tt = torch.tensor([ms, ms_e2e, ms_u8 if ms_u8 is not None else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(tt[0]), float(tt[1])
+        if ms_u8 is not None:
+            ms_u8 = float(tt[2])
 
     if rank != 0:
         return teardown(dist, world)
@@ -647,6 +698,11 @@ def main():
                    'l2_policy': 'inputs_exceed_l2 (clip batch 154 MB, activations > 1 GB vs 126 MB L2)'},
         'e2e': {'value': clips / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
+        'e2e_uint8_frames': None if ms_u8 is None else {
+            'value': clips / (ms_u8 / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_u8, 'd2h_bytes_per_step': 4,
+            'ms_per_step': ms_u8 / args.steps,
+            'what': 'same step fed with pinned uint8 256x256 frames + per-clip crop window / flip: crop, flip, ToTensor(255) and '
+                    'Normalize run on the device (input_pipeline.UInt8Clips), 3x fewer bytes over PCIe'},
         'gpu_launches': int(launches), 'cuda_graph': bool(use_graph), 'clocks': clocks, 'roofline': roofline,
         'cpu_baseline': cpu, 'final_loss': final_loss, 'parity': parity,
     }

@@ -43,17 +43,19 @@ def test_network_on_uint8_frames_equals_network_on_clip(dtype):
     sd = O.make_state_dict('S', 9, 1)
     y = torch.tensor([[1], [4], [7]]).cuda()
     outs = []
-    for source in ('clip', 'frames'):
+    fused = X.UInt8Clips(clips.frames, clips.crops, clips.size, clips.mean, clips.std, fused=True)
+    for source in ('clip', 'frames', 'frames_fused'):
         m = X.generate_model('S', n_classes=9, base_bn_splits=1, dropout=0.0)
         m.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in sd.items()})
         m = m.cuda().set_compute_dtype(dtype).train()
-        x = X.clip_from_uint8(clips) if source == 'clip' else clips
+        x = X.clip_from_uint8(clips) if source == 'clip' else (clips if source == 'frames' else fused)
         logits = m(x)
         torch.nn.functional.cross_entropy(logits, y).backward()
         outs.append((logits.detach().clone(), m.conv1_s.weight.grad.clone(), m.fc2.weight.grad.clone()))
-    assert torch.equal(outs[0][0], outs[1][0])               # the stem saw bit-identical input values
-    for a, b in zip(outs[0][1:], outs[1][1:]):
-        assert float((a - b).norm() / b.norm()) < 1e-5       # weight-gradient sums: fp32 reds of leaf outputs
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0])                 # the stem saw bit-identical input values
+        for a, b in zip(outs[0][1:], o[1:]):
+            assert float((a - b).norm() / b.norm()) < 1e-5   # weight-gradient sums: fp32 reds of leaf outputs
 
 
 def test_uint8_clips_validation():

@@ -140,31 +140,62 @@ extern "C" int x3d_stem_conv_s_fwd_u8(const uint8_t* src, const x3d_crop_t* crop
   return 0;
 }
 
-// uint8 frames -> the fp32 NCDHW clip the reference's transforms produce (crop, flip, ToTensor(255), Normalize)
-__global__ void clip_u8_to_f32_kernel(const SrcU8 x, float* __restrict__ dst, int T_, int S, int64_t total) {
+// uint8 frames -> the fp32 NCDHW clip the reference's transforms produce (crop, flip, ToTensor(255), Normalize).
+// The 3 x 256 possible results are tabulated per CTA with the reference's exact fp32 operations; a thread then turns 4
+// consecutive pixels (12 source bytes) into one float4 per channel.
+__global__ void __launch_bounds__(256) clip_u8_to_f32_kernel(const SrcU8 x, float* __restrict__ dst, int T_, int S,
+                                                             int64_t quads) {
   x3d::pdl_prologue();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ww = (int)(i % S);
-    int64_t r = i / S;
+  __shared__ float lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    const int ci = i >> 8, v = i & 255;
+    lut[ci][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, x.norm), x.mean[ci]), x.stdv[ci]);
+  }
+  __syncthreads();
+  const int qpr = (S + 3) >> 2;                                  // quads per output row
+  const int64_t plane = (int64_t)T_ * S * S;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
+    const int wq = (int)(q % qpr);
+    int64_t r = q / qpr;
     const int hh = (int)(r % S);
     r /= S;
     const int t = (int)(r % T_);
-    r /= T_;
-    const int ci = (int)(r % 3);
-    const int64_t n = r / 3;
-    dst[i] = x(n, ci, t, hh, ww);
+    const int64_t n = r / T_;
+    const x3d_crop_t c = x.crops[n];
+    const int ww0 = wq * 4;
+    const unsigned char* row = x.src + (((int64_t)n * x.T + t) * x.Hs + (c.y1 + hh)) * x.Ws * 3;
+    float o[3][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ww = ww0 + e < S ? ww0 + e : S - 1;
+      const int xs = c.flip ? c.x1 + S - 1 - ww : c.x1 + ww;
+      const unsigned char* px = row + xs * 3;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) o[ci][e] = lut[ci][__ldg(px + ci)];
+    }
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      float* d = dst + (n * 3 + ci) * plane + ((int64_t)t * S + hh) * S + ww0;
+      if (ww0 + 3 < S && (S & 3) == 0) {
+        *reinterpret_cast<float4*>(d) = make_float4(o[ci][0], o[ci][1], o[ci][2], o[ci][3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (ww0 + e < S) d[e] = o[ci][e];
+      }
+    }
   }
 }
 extern "C" int x3d_clip_u8_to_f32(const uint8_t* src, const x3d_crop_t* crops_dev, float* dst, int64_t N, int64_t T_,
                                   int64_t Hs, int64_t Ws, int64_t S, const float* mean_std, float norm_value,
                                   x3d_stream_t stream) {
   X3D_CHECK_ARG(S >= 1 && S <= Hs && S <= Ws && mean_std != nullptr && crops_dev != nullptr, "crop larger than the frames");
-  const int64_t total = N * 3 * T_ * S * S;
-  if (total == 0) return 0;
+  const int64_t quads = N * T_ * S * ((S + 3) / 4);
+  if (quads == 0) return 0;
   const SrcU8 srcx = make_src_u8(src, crops_dev, T_, Hs, Ws, S, mean_std, norm_value);
-  int64_t blocks = cdiv(total, 256);
-  if (blocks > 32 * kNumSMs) blocks = 32 * kNumSMs;
-  x3d::launch(clip_u8_to_f32_kernel, (unsigned)blocks, 256, 0, as_stream(stream), srcx, dst, (int)T_, (int)S, total);
+  int64_t blocks = cdiv(quads, 256);
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+  x3d::launch(clip_u8_to_f32_kernel, (unsigned)blocks, 256, 0, as_stream(stream), srcx, dst, (int)T_, (int)S, quads);
   X3D_LAUNCH_CHECK();
   return 0;
 }

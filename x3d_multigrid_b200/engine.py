@@ -670,7 +670,9 @@ class Engine:
                 dropout_mask: Optional[torch.Tensor] = None):
         """x: [B,3,T,H,W] fp32 NCDHW on CUDA -> logits ([B,C,1] or [B,C,T], fp32), saved state."""
         if isinstance(x, UInt8Clips):
-            pass                              # validated at construction
+            if not x.fused:                   # expand on the device (bit-identical to the reference's transform chain)
+                from .input_pipeline import clip_from_uint8
+                x = clip_from_uint8(x)
         else:
             if not x.is_cuda:
                 raise RuntimeError('x3d_multigrid_b200 runs on CUDA only (no CPU fallback)')

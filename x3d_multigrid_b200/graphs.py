@@ -36,14 +36,20 @@ class GraphedTrainStep:
         if warmup < 1:
             # the first optimizer step initialises the momentum buffers (first_step is baked into a capture)
             raise ValueError('GraphedTrainStep needs warmup >= 1')
-        dev = example_x.device
+        dev = example_x.device if isinstance(example_x.device, torch.device) else torch.device(example_x.device)
         # the warm-up steps below are real training steps on the example batch; with preserve_state the parameters,
         # BN buffers and momentum buffers are put back afterwards (in place: the graph keeps their addresses)
         snap = self._snapshot() if preserve_state else None
-        self.static_x = torch.empty_like(example_x, device=dev)
+        from .input_pipeline import UInt8Clips
         self.static_y = torch.empty_like(example_y, device=dev)
-        self.static_x.copy_(example_x)
         self.static_y.copy_(example_y)
+        if isinstance(example_x, UInt8Clips):
+            # decoded uint8 frames: the graph reads static frame / crop-table buffers through the fused stem kernels
+            self.static_x = UInt8Clips(example_x.frames.clone(), example_x.crops.clone(), example_x.size, example_x.mean,
+                                       example_x.std, example_x.norm_value)
+        else:
+            self.static_x = torch.empty_like(example_x, device=dev)
+            self.static_x.copy_(example_x)
         # warm-up on a side stream (allocator pools, parameter tables, kernel attributes, arena sizes)
         s = torch.cuda.Stream(dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -108,7 +114,14 @@ class GraphedTrainStep:
     def __call__(self, x, y):
         if x.shape != self.static_x.shape:
             raise RuntimeError('GraphedTrainStep is bound to one clip shape; keep one instance per multigrid shape')
-        self.static_x.copy_(x, non_blocking=True)
+        from .input_pipeline import UInt8Clips
+        if isinstance(self.static_x, UInt8Clips):
+            if not isinstance(x, UInt8Clips) or x.frames.shape != self.static_x.frames.shape:
+                raise RuntimeError('this step was captured for uint8 frames of another geometry')
+            self.static_x.frames.copy_(x.frames, non_blocking=True)
+            self.static_x.crops.copy_(x.crops, non_blocking=True)
+        else:
+            self.static_x.copy_(x, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
         return self.replay()
 

@@ -8,8 +8,10 @@ The reference prepares every clip on CPU workers (12 of them, train_x3d_kinetics
 normalisation happen on the device with the reference's exact fp32 arithmetic:
 
 * ``clip_from_uint8`` materialises the fp32 NCDHW clip (drop-in input for ``ResNet.forward``);
-* ``UInt8Clips`` handed to ``ResNet.forward`` instead of a tensor makes the stem kernels (conv1_s forward and weight
-  gradient) read the frames directly -- the fp32 clip never exists.
+* ``UInt8Clips`` handed to ``ResNet.forward`` instead of a tensor: the clip crosses PCIe as uint8 and is expanded on
+  the device (one kernel, bit-identical to the reference's transforms); with ``fused=True`` the stem kernels (conv1_s
+  forward and weight gradient) read the frames directly and the fp32 clip never exists (saves 154 MB of HBM per
+  16-clip batch at the price of slower, byte-granular stem kernels).
 
 The resize of the window to the crop size (PIL's antialiased bilinear filter) is NOT done here: frames are expected at
 the scale the crop is taken at (decoder- or loader-side resize); windows are S x S pixels of the source frames."""
@@ -48,6 +50,9 @@ class UInt8Clips:
     mean: Sequence[float] = KINETICS_MEAN
     std: Sequence[float] = KINETICS_STD
     norm_value: float = 255.0
+    fused: bool = False       # True: conv1_s reads the frames directly (no fp32 clip in HBM at all, but byte-granular
+                              # loads make the stem kernels ~1 ms slower per 16-clip step); False (default): ONE kernel
+                              # materialises the fp32 clip on the device (50 us), then the regular stem kernels run
 
     def __post_init__(self):
         f = self.frames
