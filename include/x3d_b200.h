@@ -244,6 +244,14 @@ int x3d_bn_relu_pool_bwd_apply(const void* a5, const float* scale, const float* 
 int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
                    float* C, int64_t ldc, int64_t M, int64_t Nn, int64_t K, const float* bias, int relu,
                    const float* mul, int accumulate, x3d_stream_t stream);
+/* Same GEMM with K split over CTAs (the head has 7 - 32 column tiles and K up to 2048: without the split a handful of CTAs
+ * walk the whole K).  Slice partials go through `ws`; the last CTA of a tile adds them in slice order (deterministic).
+ * ws: 16-byte aligned, >= x3d_small_gemm_workspace_bytes(M, Nn, K) for the full split (less = fewer slices), its first
+ * 4 KB (tile tickets) ZERO before the first call -- every call leaves them zero again.  One workspace per stream. */
+int x3d_small_gemm_ws(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
+                      float* C, int64_t ldc, int64_t M, int64_t Nn, int64_t K, const float* bias, int relu,
+                      const float* mul, int accumulate, void* ws, int64_t ws_bytes, x3d_stream_t stream);
+int64_t x3d_small_gemm_workspace_bytes(int64_t M, int64_t Nn, int64_t K);
 /* dst[j] += sum_i src[i][j] (bias gradients) */
 int x3d_colsum(const float* src, int64_t M, int64_t Nn, float* dst, x3d_stream_t stream);
 /* dst = src * (ref > 0) * mul  (ReLU + dropout backward on the [R][2048] head activations) */

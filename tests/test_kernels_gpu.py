@@ -478,3 +478,56 @@ def test_small_gemm_and_sgd():
         L().call('x3d_sgd_step', dev.data_ptr(), 1, 1000, 0.1, 0.9, 5e-5, 1.0, 1 if step == 0 else 0, stream())
         torch.cuda.synchronize()
     assert rel(p, ref_p.detach()) < 1e-6
+
+
+@pytest.mark.parametrize('R', [16, 24, 64, 200])
+def test_head_gemms_split_k(R):
+    """The six fc1 / fc2 GEMMs of the X3D-M head (x3d.py:338-345) through x3d_small_gemm_ws at the production widths
+    (432 -> 2048 -> 400): values against fp64, bit-identical from call to call (ordered split-K reduction), the
+    workspace tickets back at zero, and the same answer as the workspace-free entry point."""
+    C5, F1, ncls = 432, 2048, 400
+    g = torch.Generator().manual_seed(R)
+    pooled = torch.randn(R, C5, generator=g).cuda()
+    w1 = (torch.randn(F1, C5, generator=g) * 0.05).cuda()
+    w2 = (torch.randn(ncls, F1, generator=g) * 0.05).cuda()
+    b2 = torch.randn(ncls, generator=g).cuda()
+    dl = torch.randn(R, ncls, generator=g).cuda()
+    msk = (torch.rand(R, F1, generator=g) > 0.5).float().cuda() * 2
+    ws = torch.zeros(16 << 20, dtype=torch.uint8, device='cuda')
+    need = L().fn['x3d_small_gemm_workspace_bytes'](R, ncls, F1)
+    assert 4096 < need <= ws.numel()
+
+    def gemm(args, out_shape, accumulate=False):
+        outs = []
+        for use_ws in (True, True, False):
+            out = torch.full(out_shape, 0.5 if accumulate else float('nan'), device='cuda')
+            if use_ws:
+                L().call('x3d_small_gemm_ws', *args(out), ws.data_ptr(), ws.numel(), stream())
+            else:
+                L().call('x3d_small_gemm', *args(out), stream())
+            outs.append(out)
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1]), 'split-K result differs between two identical calls'
+        assert int(ws[:4096].view(torch.int32).abs().sum()) == 0, 'tickets not reset'
+        assert rel(outs[0], outs[2]) < 1e-6
+        return outs[0]
+
+    p = lambda t: t.data_ptr()
+    h1 = gemm(lambda o: (p(pooled), C5, 1, p(w1), 1, C5, p(o), F1, R, F1, C5, None, 1, p(msk), 0), (R, F1))
+    assert rel(h1, torch.relu(pooled.double() @ w1.double().t()) * msk.double()) < 1e-6
+    lg = gemm(lambda o: (p(h1), F1, 1, p(w2), 1, F1, p(o), ncls, R, ncls, F1, p(b2), 0, None, 0), (R, ncls))
+    assert rel(lg, h1.double() @ w2.double().t() + b2.double()) < 1e-6
+    g2 = gemm(lambda o: (p(dl), 1, ncls, p(h1), F1, 1, p(o), F1, ncls, F1, R, None, 0, None, 1), (ncls, F1), True)
+    assert rel(g2, 0.5 + dl.double().t() @ h1.double()) < 1e-6
+    dh = gemm(lambda o: (p(dl), ncls, 1, p(w2), F1, 1, p(o), F1, R, F1, ncls, None, 0, None, 0), (R, F1))
+    assert rel(dh, dl.double() @ w2.double()) < 1e-6
+    g1 = gemm(lambda o: (p(dh), 1, F1, p(pooled), C5, 1, p(o), C5, F1, C5, R, None, 0, None, 1), (F1, C5), True)
+    assert rel(g1, 0.5 + dh.double().t() @ pooled.double()) < 1e-6
+    dp = gemm(lambda o: (p(dh), F1, 1, p(w1), C5, 1, p(o), C5, R, C5, F1, None, 0, None, 0), (R, C5))
+    assert rel(dp, dh.double() @ w1.double()) < 1e-6
+    # a workspace that only holds the tickets degrades to no split, not to an error
+    tiny = torch.zeros(4096, dtype=torch.uint8, device='cuda')
+    out = torch.empty(R, C5, device='cuda')
+    L().call('x3d_small_gemm_ws', p(dh), F1, 1, p(w1), C5, 1, p(out), C5, R, C5, F1, None, 0, None, 0, tiny.data_ptr(), 4096,
+             stream())
+    assert rel(out, dp) < 1e-6

@@ -184,7 +184,8 @@ __device__ __forceinline__ void sum_split(const double* __restrict__ stats, int 
   s2 = (a1 + b1) + (c1 + d1);
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int splits, double P, int C, int Cp,
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int splits, double inv_m, double unbias, int C,
+                                   int Cp,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ run_mean, float* __restrict__ run_var,
                                    int64_t* __restrict__ nbt, float momentum, float eps,
@@ -201,11 +202,16 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int 
   }
   double s1, s2;
   sum_split(stats, N, splits, b, c, Cp, s1, s2);
-  const double m = (double)(N / splits) * P;
-  const double mu = s1 / m;
-  double var = s2 / m - mu * mu;
+  // No fp64 division / square root here (software sequences of a few hundred cycles each on this part, and this
+  // kernel sits between every conv and its consumer): 1/m and m/(m-1) come from the host, and rstd -- stored as fp32
+  // anyway -- is rsqrtf refined by one Newton step (<= 1 ulp of fp32).
+  const double mu = s1 * inv_m;
+  double var = s2 * inv_m - mu * mu;
   if (var < 0.0) var = 0.0;
-  const double r = 1.0 / sqrt(var + (double)eps);
+  const float vf = (float)(var + (double)eps);
+  float rf = rsqrtf(vf);
+  rf = rf * fmaf(-0.5f * vf * rf, rf, 1.5f);
+  const double r = (double)rf;
   const float sc = (float)((double)gamma[c] * r);
   scale[idx] = sc;
   shift[idx] = (float)((double)beta[c] - mu * (double)gamma[c] * r);
@@ -213,7 +219,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int N, int 
   rstd_o[idx] = (float)r;
   if (run_mean) {
     const int ri = b * C + c;  // x3d.py:50: channel index of the (n//s, c*s) view is b*C + c
-    const double unb = m > 1.0 ? var * m / (m - 1.0) : var;
+    const double unb = var * unbias;
     run_mean[ri] = (float)((1.0 - momentum) * (double)run_mean[ri] + momentum * mu);
     run_var[ri] = (float)((1.0 - momentum) * (double)run_var[ri] + momentum * unb);
   }
@@ -224,9 +230,10 @@ extern "C" int x3d_bn_finalize(const double* stats, int64_t N, int splits, int64
                                float* mean, float* rstd, x3d_stream_t stream) {
   X3D_CHECK_ARG(splits >= 1 && N % splits == 0, "batch must be divisible by num_splits (x3d.py:50)");
   int total = (int)(splits * Cp);
-  x3d::launch(bn_finalize_kernel, (unsigned)cdiv(total, 128), 128, 0, as_stream(stream), 
-      stats, (int)N, splits, (double)P, (int)C, (int)Cp, gamma, beta, run_mean, run_var, nbt, momentum, eps, scale,
-      shift, mean, rstd);
+  const double m = (double)(N / splits) * (double)P;
+  x3d::launch(bn_finalize_kernel, (unsigned)cdiv(total, 64), 64, 0, as_stream(stream),
+      stats, (int)N, splits, 1.0 / m, m > 1.0 ? m / (m - 1.0) : 1.0, (int)C, (int)Cp, gamma, beta, run_mean, run_var, nbt,
+      momentum, eps, scale, shift, mean, rstd);
   X3D_LAUNCH_CHECK();
   return 0;
 }
@@ -418,7 +425,7 @@ extern "C" int x3d_bn_bwd_reduce_store(const void* dout, const void* mask_out, c
 }
 
 // coefficients: da = A*dpre + B*a + Cc.  One thread per channel, loops splits and samples.
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int N, int splits, double P, int C, int Cp,
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int N, int splits, double inv_m, int C, int Cp,
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ rstd, int train, float* __restrict__ coef,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -433,14 +440,13 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int N, 
     return;
   }
   const double g = gamma[c];
-  const double m = (double)(N / splits) * P;
   double s1, s2;
   sum_split(stats, N, splits, b, c, Cp, s1, s2);
   const double mu = mean[idx], r = rstd[idx];
   const double sxh = (s2 - mu * s1) * r;  // sum dpre * xhat
   double A = g * r, B = 0.0, Cc = 0.0;
   if (train) {
-    const double m1 = s1 / m, m2 = sxh / m;
+    const double m1 = s1 * inv_m, m2 = sxh * inv_m;   // 1/m from the host: no fp64 division
     B = -g * r * r * m2;
     Cc = g * r * (-m1 + mu * r * m2);
   }
@@ -453,7 +459,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ stats, int N, 
 extern "C" int x3d_bn_bwd_finalize(const double* stats, int64_t N, int splits, int64_t P, int64_t C, int64_t Cp,
                                    const float* gamma, const float* mean, const float* rstd, int train,
                                    float* coef, float* dgamma, float* dbeta, x3d_stream_t stream) {
-  x3d::launch(bn_bwd_finalize_kernel, (unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream), stats, (int)N, splits, (double)P, (int)C,
+  x3d::launch(bn_bwd_finalize_kernel, (unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream), stats, (int)N, splits,
+              1.0 / ((double)(N / splits) * (double)P), (int)C,
                                                                             (int)Cp, gamma, mean, rstd, train, coef,
                                                                             dgamma, dbeta);
   X3D_LAUNCH_CHECK();
@@ -767,7 +774,7 @@ extern "C" int x3d_swish_gate_bwd_reduce(const void* dv, const void* a2, const f
 // no atomics -- with the 64-256 clips per GPU of the multigrid shapes, N blocks hammering the same C x w addresses
 // took 38 us per SE block).  u = scale*a2+shift (bn2 output), z = gate*u, dz = dv*swish'(z).
 __global__ void se_bwd_sample_kernel(const double* __restrict__ fwd_stats, const double* __restrict__ bwd_stats,
-                                     int splits, double P, int C, int Cp, int sw, const float* __restrict__ scale,
+                                     int splits, double inv_P, int C, int Cp, int sw, const float* __restrict__ scale,
                                      const float* __restrict__ shift, const float* __restrict__ W1,
                                      const float* __restrict__ W2, const float* __restrict__ hidden,
                                      const float* __restrict__ gate, float* __restrict__ work,
@@ -811,7 +818,7 @@ __global__ void se_bwd_sample_kernel(const double* __restrict__ fwd_stats, const
     if (c < C) {
       float dp = 0.f;
       for (int j = 0; j < sw; ++j) dp = fmaf(W1[(int64_t)j * C + c], s_dz1[j], dp);
-      dpP = (float)((double)dp / P);
+      dpP = (float)((double)dp * inv_P);
     }
     work[(int64_t)n * Cp + c] = dpP;
   }
@@ -861,9 +868,9 @@ __global__ void se_param_grad_kernel(const float* __restrict__ dz2, const float*
 
 // BN2 backward coefficients per (n, c): da2 = E1*dz + E2*a2 + E3, with du = dz*g + dpP.
 __global__ void se_bn_bwd_coef_kernel(const double* __restrict__ fwd_stats, const double* __restrict__ bwd_stats,
-                                      int N, int splits, double P, int C, int Cp, const float* __restrict__ gamma,
-                                      const float* __restrict__ mean, const float* __restrict__ rstd, int train,
-                                      const float* __restrict__ gate /*nullable*/, const float* __restrict__ work,
+                                      int N, int splits, double P, double inv_m, int C, int Cp,
+                                      const float* __restrict__ gamma, const float* __restrict__ mean,
+                                      const float* __restrict__ rstd, int train, const float* __restrict__ gate /*nullable*/, const float* __restrict__ work,
                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
                                       float* __restrict__ coef) {
   x3d::pdl_prologue();
@@ -880,7 +887,6 @@ __global__ void se_bn_bwd_coef_kernel(const double* __restrict__ fwd_stats, cons
     return;
   }
   const double gm = gamma[c];
-  const double m = (double)(N / splits) * P;
   double s1 = 0.0, s2 = 0.0;   // sum du, sum du*a2 over the split (du = dz*gate + dp/P)
   if (gate) {
 #pragma unroll 4
@@ -898,7 +904,7 @@ __global__ void se_bn_bwd_coef_kernel(const double* __restrict__ fwd_stats, cons
   const double sxh = (s2 - mu * s1) * r;
   double A = gm * r, B = 0.0, Cc = 0.0;
   if (train) {
-    const double m1 = s1 / m, m2 = sxh / m;
+    const double m1 = s1 * inv_m, m2 = sxh * inv_m;   // 1/m from the host: no fp64 division
     B = -gm * r * r * m2;
     Cc = gm * r * (-m1 + mu * r * m2);
   }
@@ -925,7 +931,7 @@ extern "C" int x3d_se_bn_bwd(const double* fwd_stats, const double* bwd_stats, i
     size_t smem = (C + 2 * sw) * sizeof(float);
     float* dz2 = work + N * Cp;                 // work: [N][Cp] dp/P | [N][Cp] dz2 | [N][sw] dz1
     float* dz1 = dz2 + N * Cp;
-    x3d::launch(se_bwd_sample_kernel, (unsigned)N, 256, smem, as_stream(stream), fwd_stats, bwd_stats, splits, (double)P, (int)C,
+    x3d::launch(se_bwd_sample_kernel, (unsigned)N, 256, smem, as_stream(stream), fwd_stats, bwd_stats, splits, 1.0 / (double)P, (int)C,
                 (int)Cp, sw, scale, shift, W1, W2, hidden, gate, work, dz2, dz1);
     X3D_LAUNCH_CHECK();
     const int64_t outs = 2 * C * sw + C + sw;
@@ -934,8 +940,8 @@ extern "C" int x3d_se_bn_bwd(const double* fwd_stats, const double* bwd_stats, i
     X3D_LAUNCH_CHECK();
   }
   x3d::launch(se_bn_bwd_coef_kernel, (unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream), fwd_stats, bwd_stats, (int)N, splits,
-                                                                           (double)P, (int)C, (int)Cp, gamma, mean, rstd,
-                                                                           train, gate, work, dgamma, dbeta, coef);
+              (double)P, 1.0 / ((double)(N / splits) * (double)P), (int)C, (int)Cp, gamma, mean, rstd, train, gate, work,
+              dgamma, dbeta, coef);
   X3D_LAUNCH_CHECK();
   return 0;
 }
@@ -1232,34 +1238,156 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const float* __restrict
     }
   }
 }
-// skinny variants for M <= 32 rows (the head: M = batch): the 32x32-tile kernel would run on a handful of CTAs
-// (a) B k-contiguous (sbk == 1): one warp per output column, lanes split K, shuffle reduction
-template <int MR>
-__global__ void skinny_gemm_kcontig_kernel(const float* __restrict__ A, int64_t sai, int64_t sak,
-                                           const float* __restrict__ B, int64_t sbj, float* __restrict__ C, int64_t ldc,
-                                           int M, int Nn, int K, const float* __restrict__ bias, int relu,
-                                           const float* __restrict__ mul, int accumulate) {
+// Split-K flavour of the tile kernel (the head GEMMs have 7 - 32 column tiles and K up to 2048: without a K split a
+// handful of CTAs walk 128 dependent k-tiles -- fc1 dgrad at 64 rows took 228 us for 0.1 GFLOP).  grid.z CTAs share a
+// tile, each reduces one K slice (operands of the next k-tile are fetched into registers while the current one is
+// multiplied) and parks its 64 x 64 partial in the caller's workspace; the CTA that arrives last at the tile's ticket adds
+// the partials IN SLICE ORDER (deterministic) and runs the epilogue.  Tickets are left at zero for the next call.
+__global__ void __launch_bounds__(256)
+small_gemm_splitk_kernel(const float* __restrict__ A, int64_t sai, int64_t sak, const float* __restrict__ B, int64_t sbk,
+                         int64_t sbj, float* __restrict__ C, int64_t ldc, int M, int Nn, int K, int kchunk,
+                         const float* __restrict__ bias, int relu, const float* __restrict__ mul, int accumulate,
+                         float* __restrict__ part, unsigned* __restrict__ tickets) {
   x3d::pdl_prologue();
-  // one warp per JW output columns: the MR values of A for a k are loaded once and feed JW x MR FMAs
+  // A K slice is consumed in stages of 64: ALL 32 loads of a thread for a stage are issued back to back (the kernel is
+  // latency-bound: 3.5 MB of weights, a few microseconds), the next stage's loads fly while this one is multiplied.
+  constexpr int TM = 64, TN = 64, TK = 64, PER = TM * TK / 256;
+  __shared__ __align__(16) float As[TK][TM + 4];  // [k][i]
+  __shared__ __align__(16) float Bs[TK][TN + 4];  // [k][j]
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int i0 = blockIdx.y * TM, j0 = blockIdx.x * TN;
+  const int S = gridDim.z, sl = blockIdx.z;
+  const int kbeg = sl * kchunk, kend = min(K, kbeg + kchunk);
+  // element e of a thread: q = tid + 256 e; the fastest thread index follows the operand's unit-stride dimension
+  const bool a_kfast = sak == 1, b_kfast = sbk == 1;
+  float ra[PER], rb[PER];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+      const int q = tid + e * 256;
+      const int ai = a_kfast ? q / TK : q % TM, ak = a_kfast ? q % TK : q / TM;
+      const int bj = b_kfast ? q / TK : q % TN, bk = b_kfast ? q % TK : q / TN;
+      ra[e] = (i0 + ai < M && k0 + ak < kend) ? __ldg(&A[(int64_t)(i0 + ai) * sai + (int64_t)(k0 + ak) * sak]) : 0.f;
+      rb[e] = (j0 + bj < Nn && k0 + bk < kend) ? __ldg(&B[(int64_t)(k0 + bk) * sbk + (int64_t)(j0 + bj) * sbj]) : 0.f;
+    }
+  };
+  auto park = [&]() {
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+      const int q = tid + e * 256;
+      const int ai = a_kfast ? q / TK : q % TM, ak = a_kfast ? q % TK : q / TM;
+      const int bj = b_kfast ? q / TK : q % TN, bk = b_kfast ? q % TK : q / TN;
+      As[ak][ai] = ra[e];
+      Bs[bk][bj] = rb[e];
+    }
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  if (kbeg < kend) fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += TK) {
+    park();
+    __syncthreads();
+    if (k0 + TK < kend) fetch(k0 + TK);
+    const int kn = min(TK, kend - k0);
+#pragma unroll 8
+    for (int k = 0; k < kn; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+  if (S > 1) {
+    float4* mine = reinterpret_cast<float4*>(part + ((size_t)sl * gridDim.x * gridDim.y + tile) * (TM * TN)) + tid * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) __stcg(mine + i, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&tickets[tile], 1u) == (unsigned)(S - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int s2 = 0; s2 < S; ++s2) {       // fixed order: bit-identical from run to run
+      const float4* src = reinterpret_cast<const float4*>(part + ((size_t)s2 * gridDim.x * gridDim.y + tile) * (TM * TN)) + tid * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldcg(src + i);
+        acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+      }
+    }
+    if (tid == 0) tickets[tile] = 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ii = i0 + ty * 4 + i;
+    if (ii >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int jj = j0 + tx * 4 + j;
+      if (jj >= Nn) continue;
+      float v = acc[i][j] + (bias ? bias[jj] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      if (mul) v *= mul[(int64_t)ii * Nn + jj];
+      float* dst = &C[(int64_t)ii * ldc + jj];
+      *dst = accumulate ? (*dst + v) : v;
+    }
+  }
+}
+constexpr int64_t kGemmTicketBytes = 4096;     // 1024 tile tickets at the head of the workspace
+
+// skinny variants for M <= 32 rows (the head: M = batch).  The weight matrix (N x K, 3.5 MB for fc1 / fc2 of X3D-M) is the
+// only real traffic; what matters is that enough CTAs pull on it at once and that no thread walks a long serial K loop
+// (fc1 dgrad with 14 CTAs x 128 dependent iterations took 115 us for 3.5 MB).  Both variants are deterministic.
+// (a) B k-contiguous (sbk == 1): a warp owns JW output columns and one of KW slices of K (lanes stride through the
+//     slice, shuffle reduction); the KW slice results of a column group are added in a fixed order through shared memory
+template <int MR>
+__global__ void __launch_bounds__(256)
+skinny_gemm_kcontig_kernel(const float* __restrict__ A, int64_t sai, int64_t sak, const float* __restrict__ B, int64_t sbj,
+                           float* __restrict__ C, int64_t ldc, int M, int Nn, int K, int KW, const float* __restrict__ bias,
+                           int relu, const float* __restrict__ mul, int accumulate) {
+  x3d::pdl_prologue();
   constexpr int JW = MR <= 16 ? 4 : 2;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
-  const int j0 = warp * JW;
-  if (j0 >= Nn) return;
+  __shared__ float red[8][JW * MR];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gpb = 8 / KW;                                       // column groups per block
+  const int grp = wib / KW, ks = wib - grp * KW;
+  const int j0 = (blockIdx.x * gpb + grp) * JW;
+  const int kchunk = ((K + KW - 1) / KW + 31) / 32 * 32;
+  const int kbeg = ks * kchunk, kend = min(K, kbeg + kchunk);
   float acc[JW][MR];
 #pragma unroll
   for (int q = 0; q < JW; ++q)
 #pragma unroll
     for (int i = 0; i < MR; ++i) acc[q][i] = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    float a[MR], b[JW];
+  if (j0 < Nn) {
+#pragma unroll 2
+    for (int k = kbeg + lane; k < kend; k += 32) {
+      float a[MR], b[JW];
 #pragma unroll
-    for (int q = 0; q < JW; ++q) b[q] = (j0 + q < Nn) ? B[(int64_t)(j0 + q) * sbj + k] : 0.f;
+      for (int q = 0; q < JW; ++q) b[q] = (j0 + q < Nn) ? __ldg(&B[(int64_t)(j0 + q) * sbj + k]) : 0.f;
 #pragma unroll
-    for (int i = 0; i < MR; ++i) a[i] = (i < M) ? A[(int64_t)i * sai + (int64_t)k * sak] : 0.f;
+      for (int i = 0; i < MR; ++i) a[i] = (i < M) ? __ldg(&A[(int64_t)i * sai + (int64_t)k * sak]) : 0.f;
 #pragma unroll
-    for (int q = 0; q < JW; ++q)
+      for (int q = 0; q < JW; ++q)
 #pragma unroll
-      for (int i = 0; i < MR; ++i) acc[q][i] = fmaf(a[i], b[q], acc[q][i]);
+        for (int i = 0; i < MR; ++i) acc[q][i] = fmaf(a[i], b[q], acc[q][i]);
+    }
   }
 #pragma unroll
   for (int q = 0; q < JW; ++q)
@@ -1268,58 +1396,65 @@ __global__ void skinny_gemm_kcontig_kernel(const float* __restrict__ A, int64_t 
 #pragma unroll
       for (int o = 16; o; o >>= 1) acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], o);
     }
-  if (lane == 0) {
+  // every lane now holds all JW*MR sums of its warp; lane e keeps element e (and e+32, ...)
 #pragma unroll
-    for (int q = 0; q < JW; ++q) {
-      const int j = j0 + q;
-      if (j >= Nn) break;
+  for (int q = 0; q < JW; ++q)
 #pragma unroll
-      for (int i = 0; i < MR; ++i) {
-        if (i < M) {
-          float v = acc[q][i] + (bias ? bias[j] : 0.f);
-          if (relu) v = fmaxf(v, 0.f);
-          if (mul) v *= mul[(int64_t)i * Nn + j];
-          float* dst = &C[(int64_t)i * ldc + j];
-          *dst = accumulate ? (*dst + v) : v;
-        }
-      }
-    }
+    for (int i = 0; i < MR; ++i)
+      if (((q * MR + i) & 31) == lane) red[wib][q * MR + i] = acc[q][i];
+  __syncthreads();
+  for (int e = threadIdx.x; e < gpb * JW * MR; e += 256) {
+    const int g = e / (JW * MR), r = e - g * (JW * MR);
+    const int q = r / MR, i = r - q * MR;
+    const int j = (blockIdx.x * gpb + g) * JW + q;
+    if (j >= Nn || i >= M) continue;
+    float v = 0.f;
+    for (int s2 = 0; s2 < KW; ++s2) v += red[g * KW + s2][r];
+    v += bias ? bias[j] : 0.f;
+    if (relu) v = fmaxf(v, 0.f);
+    if (mul) v *= mul[(int64_t)i * Nn + j];
+    float* dst = &C[(int64_t)i * ldc + j];
+    *dst = accumulate ? (*dst + v) : v;
   }
 }
-// (b) B j-contiguous (sbj == 1): block = 32 output columns x 8 k-slices; every thread walks its slice of K for its
-//     column (coalesced over the columns), the 8 slices are added in a fixed order through shared memory -- no
-//     atomics: dh / dpooled of the head backward feed the whole backward pass (see bn_relu_pool_fwd_kernel).
-template <int MR>
-__global__ void skinny_gemm_jcontig_kernel(const float* __restrict__ A, int64_t sai, int64_t sak,
-                                           const float* __restrict__ B, int64_t sbk, float* __restrict__ C, int64_t ldc,
-                                           int M, int Nn, int K, int accumulate) {
+// (b) B j-contiguous (sbj == 1): block = CW output columns x 512 / CW k-slices; every thread walks its slice of K for its
+//     column, the slices are added in a fixed order through shared memory -- no atomics: dh / dpooled of the head
+//     backward feed the whole backward pass (see bn_relu_pool_fwd_kernel).  CW = 8 when 32-column blocks would leave
+//     most SMs idle (a 32-byte row segment per k is still a full DRAM sector).
+template <int MR, int CW>
+__global__ void __launch_bounds__(512)
+skinny_gemm_jcontig_kernel(const float* __restrict__ A, int64_t sai, int64_t sak, const float* __restrict__ B, int64_t sbk,
+                           float* __restrict__ C, int64_t ldc, int M, int Nn, int K, int accumulate) {
   x3d::pdl_prologue();
-  constexpr int SL = MR <= 16 ? 16 : 8;                         // k slices (shared scratch <= 34 KB)
-  __shared__ float red[SL][MR][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x SL
-  const int j = blockIdx.x * 32 + tx;
+  constexpr int SL = (MR <= 16 ? 512 : 256) / CW;              // k slices (shared scratch <= 37 KB)
+  __shared__ float red[SL][MR][CW + 1];
+  const int tx = threadIdx.x % CW, ty = threadIdx.x / CW;      // CW x SL
+  const int j = blockIdx.x * CW + tx;
   const int kchunk = (K + SL - 1) / SL;
   const int k0 = ty * kchunk;
   const int k1 = k0 + kchunk < K ? k0 + kchunk : K;
   float acc[MR];
 #pragma unroll
   for (int i = 0; i < MR; ++i) acc[i] = 0.f;
-  if (j < Nn) {
+  if (j < Nn && ty < SL) {
+#pragma unroll 2
     for (int k = k0; k < k1; ++k) {
-      const float b = B[(int64_t)k * sbk + j];
+      const float b = __ldg(&B[(int64_t)k * sbk + j]);
 #pragma unroll
       for (int i = 0; i < MR; ++i)
         if (i < M) acc[i] = fmaf(__ldg(&A[(int64_t)i * sai + (int64_t)k * sak]), b, acc[i]);
     }
   }
+  if (ty < SL) {
 #pragma unroll
-  for (int i = 0; i < MR; ++i) red[ty][i][tx] = acc[i];
+    for (int i = 0; i < MR; ++i) red[ty][i][tx] = acc[i];
+  }
   __syncthreads();
-  for (int e = threadIdx.x; e < MR * 32; e += 32 * SL) {
-    const int i = e >> 5, c = e & 31, jj = blockIdx.x * 32 + c;
+  for (int e = threadIdx.x; e < MR * CW; e += blockDim.x) {
+    const int i = e / CW, c = e % CW, jj = blockIdx.x * CW + c;
     if (i < M && jj < Nn) {
       float v = 0.f;
-#pragma unroll
+#pragma unroll 8
       for (int q = 0; q < SL; ++q) v += red[q][i][c];
       float* dst = &C[(int64_t)i * ldc + jj];
       *dst = accumulate ? (*dst + v) : v;
@@ -1327,22 +1462,63 @@ __global__ void skinny_gemm_jcontig_kernel(const float* __restrict__ A, int64_t 
   }
 }
 
-extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
-                              float* C, int64_t ldc, int64_t M, int64_t Nn, int64_t K, const float* bias, int relu,
-                              const float* mul, int accumulate, x3d_stream_t stream) {
+// slices of K for the split-K kernel: enough CTAs for two per SM, at least 64 k per slice, capped by the workspace
+static int splitk_plan(int64_t M, int64_t Nn, int64_t K, int64_t ws_bytes, int* kchunk) {
+  const int64_t tiles = cdiv(M, 64) * cdiv(Nn, 64);
+  int64_t S = cdiv(2 * kNumSMs, tiles);
+  if (S > K / 64) S = K / 64;
+  if (S > 16) S = 16;             // the last CTA of a tile adds the slices alone: 16 x 16 KB is ~2 us of L2 reads
+  const int64_t fit = (ws_bytes - kGemmTicketBytes) / (tiles * 64 * 64 * (int64_t)sizeof(float));
+  if (S > fit) S = fit;
+  if (S < 1 || tiles > kGemmTicketBytes / 4) S = 1;
+  int64_t kc = cdiv(cdiv(K, S), 16) * 16;
+  if (kc < 16) kc = 16;
+  *kchunk = (int)kc;
+  return (int)cdiv(K, kc);
+}
+extern "C" int64_t x3d_small_gemm_workspace_bytes(int64_t M, int64_t Nn, int64_t K) {
+  const int64_t tiles = cdiv(M, 64) * cdiv(Nn, 64);
+  int64_t S = cdiv(2 * kNumSMs, tiles);
+  if (S > K / 64) S = K / 64;
+  if (S > 16) S = 16;
+  if (S < 1) S = 1;
+  return kGemmTicketBytes + S * tiles * 64 * 64 * (int64_t)sizeof(float);
+}
+// Dispatch (micro-benchmarked per flavour, tools/head_gemm_microbench.py): batch <= 32 rows -> the skinny kernels (except a
+// j-contiguous weight with K > 1024, fc1 dgrad: 49 us skinny vs 20 us split-K); enough tiles to fill the machine or a
+// K of one or two k-tiles (the weight gradients, K = batch) -> the plain tile kernel; otherwise split-K when a workspace
+// was given.
+static int small_gemm_impl(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj, float* C,
+                           int64_t ldc, int64_t M, int64_t Nn, int64_t K, const float* bias, int relu, const float* mul,
+                           int accumulate, void* ws, int64_t ws_bytes, x3d_stream_t stream) {
   if (M == 0 || Nn == 0) return 0;
+  const int64_t tiles = cdiv(M, 64) * cdiv(Nn, 64);
+  const bool can_split = ws != nullptr && tiles < kNumSMs && K > 64;
   if (M <= 32 && sbk == 1) {
-    const int64_t threads = cdiv(Nn, M <= 16 ? 4 : 2) * 32;     // JW columns per warp
-#define SK_(MR) x3d::launch(skinny_gemm_kcontig_kernel<MR>, (unsigned)cdiv(threads, 256), 256, 0, as_stream(stream),  \
-      A, sai, sak, B, sbj, C, ldc, (int)M, (int)Nn, (int)K, bias, relu, mul, accumulate)
+    const int JW = M <= 16 ? 4 : 2;
+    const int64_t groups = cdiv(Nn, JW);
+    int KW = 1;                                                  // slices of K per column group: aim at >= 8 warps per SM
+    while (KW < 8 && groups * KW < 8 * kNumSMs && K / (2 * KW) >= 64) KW *= 2;
+    const unsigned grid = (unsigned)cdiv(groups, 8 / KW);
+#define SK_(MR) x3d::launch(skinny_gemm_kcontig_kernel<MR>, grid, 256, 0, as_stream(stream),  \
+      A, sai, sak, B, sbj, C, ldc, (int)M, (int)Nn, (int)K, KW, bias, relu, mul, accumulate)
     if (M <= 8) SK_(8); else if (M <= 16) SK_(16); else SK_(32);
 #undef SK_
-  } else if (M <= 32 && sbj == 1 && !bias && !relu && !mul) {
-    dim3 grid((unsigned)cdiv(Nn, 32));
-#define SJ_(MR) x3d::launch(skinny_gemm_jcontig_kernel<MR>, grid, (MR <= 16 ? 512 : 256), 0, as_stream(stream),  \
-      A, sai, sak, B, sbk, C, ldc, (int)M, (int)Nn, (int)K, accumulate)
-    if (M <= 8) SJ_(8); else if (M <= 16) SJ_(16); else SJ_(32);
+  } else if (M <= 32 && sbj == 1 && !bias && !relu && !mul && !(can_split && K > 1024)) {
+    const bool narrow = cdiv(Nn, 32) < kNumSMs;
+#define SJ_(MR, CWv) x3d::launch(skinny_gemm_jcontig_kernel<MR, CWv>, (unsigned)cdiv(Nn, CWv), (MR <= 16 ? 512 : 256), 0,  \
+      as_stream(stream), A, sai, sak, B, sbk, C, ldc, (int)M, (int)Nn, (int)K, accumulate)
+#define SJ2_(MR) do { if (narrow) SJ_(MR, 8); else SJ_(MR, 32); } while (0)
+    if (M <= 8) SJ2_(8); else if (M <= 16) SJ2_(16); else SJ2_(32);
+#undef SJ2_
 #undef SJ_
+  } else if (can_split) {
+    int kchunk = 16;
+    const int S = splitk_plan(M, Nn, K, ws_bytes, &kchunk);
+    dim3 grid((unsigned)cdiv(Nn, 64), (unsigned)cdiv(M, 64), (unsigned)S);
+    x3d::launch(small_gemm_splitk_kernel, grid, 256, 0, as_stream(stream), A, sai, sak, B, sbk, sbj, C, ldc, (int)M, (int)Nn,
+                (int)K, kchunk, bias, relu, mul, accumulate,
+                reinterpret_cast<float*>(static_cast<char*>(ws) + kGemmTicketBytes), static_cast<unsigned*>(ws));
   } else {
     dim3 grid((unsigned)cdiv(Nn, 64), (unsigned)cdiv(M, 64));
     x3d::launch(small_gemm_kernel, grid, 256, 0, as_stream(stream), A, sai, sak, B, sbk, sbj, C, ldc, (int)M, (int)Nn, (int)K,
@@ -1350,6 +1526,18 @@ extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const fl
   }
   X3D_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int x3d_small_gemm_ws(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
+                                 float* C, int64_t ldc, int64_t M, int64_t Nn, int64_t K, const float* bias, int relu,
+                                 const float* mul, int accumulate, void* ws, int64_t ws_bytes, x3d_stream_t stream) {
+  X3D_CHECK_ARG(ws != nullptr && ws_bytes >= kGemmTicketBytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
+                "workspace must be 16-byte aligned and hold at least the 4 KB ticket area (zero-filled once by the caller)");
+  return small_gemm_impl(A, sai, sak, B, sbk, sbj, C, ldc, M, Nn, K, bias, relu, mul, accumulate, ws, ws_bytes, stream);
+}
+extern "C" int x3d_small_gemm(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
+                              float* C, int64_t ldc, int64_t M, int64_t Nn, int64_t K, const float* bias, int relu,
+                              const float* mul, int accumulate, x3d_stream_t stream) {
+  return small_gemm_impl(A, sai, sak, B, sbk, sbj, C, ldc, M, Nn, K, bias, relu, mul, accumulate, nullptr, 0, stream);
 }
 
 __global__ void colsum_kernel(const float* __restrict__ src, int M, int Nn, float* __restrict__ dst) {

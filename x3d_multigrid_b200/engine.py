@@ -148,6 +148,8 @@ class Engine:
         self.wg_ws = None
         if device.type == 'cuda' and self.dt == BF16 and not os.environ.get('X3D_WG_ATOMIC'):
             self.wg_ws = torch.empty(int(self.lib.fn['x3d_pwconv_wgrad_workspace_bytes']()), dtype=torch.uint8, device=device)
+        # split-K scratch of the fp32 head GEMMs (main stream only); its ticket area must start out zero
+        self.head_ws = torch.zeros(16 << 20, dtype=torch.uint8, device=device)
         # weight-gradient kernels feed nothing downstream: they run on a side stream, concurrently with the
         # dgrad / BN chain of the main stream (fills the SMs that the small late-stage kernels leave idle)
         self._side = torch.cuda.Stream(device) if (device.type == 'cuda' and not os.environ.get('X3D_NO_SIDE')) else None
@@ -605,12 +607,12 @@ class Engine:
                  H * W, pool_t, C5, C5p, dt, st)
         F1 = m.fc1.out_channels
         h1 = self._f32(R, F1)
-        lib.call('x3d_small_gemm', _ptr(pooled), C5, 1, self.p('fc1.weight'), 1, C5, _ptr(h1), F1, R, F1, C5, None, 1,
-                 _ptr(dropout_mask), 0, st)
+        lib.call('x3d_small_gemm_ws', _ptr(pooled), C5, 1, self.p('fc1.weight'), 1, C5, _ptr(h1), F1, R, F1, C5, None, 1,
+                 _ptr(dropout_mask), 0, self.head_ws.data_ptr(), self.head_ws.numel(), st)
         ncls = m.fc2.out_features
         logits = self._f32(R, ncls)
-        lib.call('x3d_small_gemm', _ptr(h1), F1, 1, self.p('fc2.weight'), 1, F1, _ptr(logits), ncls, R, ncls, F1,
-                 self.p('fc2.bias'), 0, None, 0, st)
+        lib.call('x3d_small_gemm_ws', _ptr(h1), F1, 1, self.p('fc2.weight'), 1, F1, _ptr(logits), ncls, R, ncls, F1,
+                 self.p('fc2.bias'), 0, None, 0, self.head_ws.data_ptr(), self.head_ws.numel(), st)
         if save is not None:
             save['head'] = (xL, geom, a5, bn5, pooled, h1, dropout_mask)
         if pool_t:
@@ -634,20 +636,20 @@ class Engine:
             dl = dlogits.permute(0, 2, 1).reshape(R, ncls)
         dl = dl.to(torch.float32).contiguous()
         # fc2
-        lib.call('x3d_small_gemm', _ptr(dl), 1, ncls, _ptr(h1), F1, 1, self.g('fc2.weight'), F1, ncls, F1, R, None, 0,
-                 None, 1, st)
+        lib.call('x3d_small_gemm_ws', _ptr(dl), 1, ncls, _ptr(h1), F1, 1, self.g('fc2.weight'), F1, ncls, F1, R, None, 0,
+                 None, 1, self.head_ws.data_ptr(), self.head_ws.numel(), st)
         lib.call('x3d_colsum', _ptr(dl), R, ncls, self.g('fc2.bias'), st)
         dh = self._f32(R, F1)
-        lib.call('x3d_small_gemm', _ptr(dl), ncls, 1, self.p('fc2.weight'), F1, 1, _ptr(dh), F1, R, F1, ncls, None, 0,
-                 None, 0, st)
+        lib.call('x3d_small_gemm_ws', _ptr(dl), ncls, 1, self.p('fc2.weight'), F1, 1, _ptr(dh), F1, R, F1, ncls, None, 0,
+                 None, 0, self.head_ws.data_ptr(), self.head_ws.numel(), st)
         dz = dh
         lib.call('x3d_relu_mask_mul', _ptr(dh), _ptr(h1), _ptr(dropout_mask), _ptr(dz), R * F1, st)
         # fc1
-        lib.call('x3d_small_gemm', _ptr(dz), 1, F1, _ptr(pooled), C5, 1, self.g('fc1.weight'), C5, F1, C5, R, None, 0,
-                 None, 1, st)
+        lib.call('x3d_small_gemm_ws', _ptr(dz), 1, F1, _ptr(pooled), C5, 1, self.g('fc1.weight'), C5, F1, C5, R, None, 0,
+                 None, 1, self.head_ws.data_ptr(), self.head_ws.numel(), st)
         dpooled = self._f32(R, C5)
-        lib.call('x3d_small_gemm', _ptr(dz), F1, 1, self.p('fc1.weight'), C5, 1, _ptr(dpooled), C5, R, C5, F1, None, 0,
-                 None, 0, st)
+        lib.call('x3d_small_gemm_ws', _ptr(dz), F1, 1, self.p('fc1.weight'), C5, 1, _ptr(dpooled), C5, R, C5, F1, None, 0,
+                 None, 0, self.head_ws.data_ptr(), self.head_ws.numel(), st)
         # relu + pool + bn5
         bst5 = self._stats(self.arena_b, N, C5p)
         lib.call('x3d_bn_relu_pool_bwd_reduce', _ptr(a5), _ptr(bn5.scale), _ptr(bn5.shift), bn5.splits, _ptr(dpooled),
