@@ -358,9 +358,10 @@ def test_split_bn_forward_backward(dtype, splits):
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('with_se', [True, False])
-def test_se_swish_forward_backward(dtype, with_se):
+@pytest.mark.parametrize('N', [4, 44])       # 44 samples: SE parameter gradients summed by lane groups (multigrid batches)
+def test_se_swish_forward_backward(dtype, with_se, N):
     """bn2 -> SE gate -> swish (x3d.py:151-160) forward and backward incl. SE/BN parameter grads."""
-    N, C, T, H, W, sw, splits = 4, 54, 2, 4, 5, 8, 2
+    C, T, H, W, sw, splits = 54, 2, 4, 5, 8, 2
     Cp, P = pad8(C), T * H * W
     a2 = (O.det_clip((N, C, T, H, W), 'sea', torch.float32) * 1.3 - 0.2).cuda()
     gamma = (1 + O.det_tensor((C,), 'seg', scale=0.2, dtype=torch.float32)).cuda()

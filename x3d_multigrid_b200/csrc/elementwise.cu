@@ -828,42 +828,53 @@ __global__ void se_bwd_sample_kernel(const double* __restrict__ fwd_stats, const
 // One thread per output element, samples added in order.
 __global__ void se_param_grad_kernel(const float* __restrict__ dz2, const float* __restrict__ dz1,
                                      const float* __restrict__ pooled, const float* __restrict__ hidden, int N, int C,
-                                     int Cp, int sw, float* __restrict__ dW1, float* __restrict__ db1,
+                                     int Cp, int sw, int G, float* __restrict__ dW1, float* __restrict__ db1,
                                      float* __restrict__ dW2, float* __restrict__ db2) {
   x3d::pdl_prologue();
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  // G (a power of two <= 32) consecutive lanes share one output: lane g takes samples g, g+G, ... (8 loads in flight per
+  // operand), then a fixed shuffle tree adds the G partial sums -- deterministic, and a multigrid batch of 256 clips is
+  // one round of loads instead of 32 dependent ones (22 us per SE block at 256 x 4 x 111^2).
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = t / G, g = t & (G - 1);
   const int nW = C * sw;
-  // dot product over the samples: 8 independent loads in flight per operand, added in sample order
   auto dot = [&](const float* __restrict__ a, int64_t sa, const float* __restrict__ b, int64_t sb) {
     float acc = 0.f;
-    int n = 0;
-    for (; n + 8 <= N; n += 8) {
+    int n = g;
+    for (; n + 7 * G < N; n += 8 * G) {
       float av[8], bv[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        av[u] = __ldg(a + (int64_t)(n + u) * sa);
-        bv[u] = b ? __ldg(b + (int64_t)(n + u) * sb) : 1.f;
+        av[u] = __ldg(a + (int64_t)(n + u * G) * sa);
+        bv[u] = b ? __ldg(b + (int64_t)(n + u * G) * sb) : 1.f;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) acc = fmaf(av[u], bv[u], acc);
     }
-    for (; n < N; ++n) acc = fmaf(__ldg(a + (int64_t)n * sa), b ? __ldg(b + (int64_t)n * sb) : 1.f, acc);
+    for (; n < N; n += G) acc = fmaf(__ldg(a + (int64_t)n * sa), b ? __ldg(b + (int64_t)n * sb) : 1.f, acc);
     return acc;
   };
+  float v = 0.f;
+  float* dst = nullptr;
   if (o < nW) {                                  // dW2[c][j]
     const int c = o / sw, j = o - c * sw;
-    dW2[o] += dot(dz2 + c, Cp, hidden + j, sw);
+    v = dot(dz2 + c, Cp, hidden + j, sw);
+    dst = dW2 + o;
   } else if (o < 2 * nW) {                       // dW1[j][c]
     const int q = o - nW;
     const int j = q / C, c = q - j * C;
-    dW1[q] += dot(dz1 + j, sw, pooled + c, C);
+    v = dot(dz1 + j, sw, pooled + c, C);
+    dst = dW1 + q;
   } else if (o < 2 * nW + C) {                   // db2[c]
     const int c = o - 2 * nW;
-    db2[c] += dot(dz2 + c, Cp, nullptr, 0);
+    v = dot(dz2 + c, Cp, nullptr, 0);
+    dst = db2 + c;
   } else if (o < 2 * nW + C + sw) {              // db1[j]
     const int j = o - 2 * nW - C;
-    db1[j] += dot(dz1 + j, sw, nullptr, 0);
+    v = dot(dz1 + j, sw, nullptr, 0);
+    dst = db1 + j;
   }
+  for (int off = G >> 1; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (dst != nullptr && g == 0) *dst += v;
 }
 
 // BN2 backward coefficients per (n, c): da2 = E1*dz + E2*a2 + E3, with du = dz*g + dpP.
@@ -935,8 +946,10 @@ extern "C" int x3d_se_bn_bwd(const double* fwd_stats, const double* bwd_stats, i
                 (int)Cp, sw, scale, shift, W1, W2, hidden, gate, work, dz2, dz1);
     X3D_LAUNCH_CHECK();
     const int64_t outs = 2 * C * sw + C + sw;
-    x3d::launch(se_param_grad_kernel, (unsigned)cdiv(outs, 128), 128, 0, as_stream(stream), (const float*)dz2, (const float*)dz1,
-                pooled, hidden, (int)N, (int)C, (int)Cp, sw, dW1, db1, dW2, db2);
+    int G = 1;                                   // lanes per output: ~8 samples per lane
+    while (G < 32 && G * 8 < N) G *= 2;
+    x3d::launch(se_param_grad_kernel, (unsigned)cdiv(outs * G, 128), 128, 0, as_stream(stream), (const float*)dz2,
+                (const float*)dz1, pooled, hidden, (int)N, (int)C, (int)Cp, sw, G, dW1, db1, dW2, db2);
     X3D_LAUNCH_CHECK();
   }
   x3d::launch(se_bn_bwd_coef_kernel, (unsigned)cdiv(splits * Cp, 64), 64, 0, as_stream(stream), fwd_stats, bwd_stats, (int)N, splits,
