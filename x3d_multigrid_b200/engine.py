@@ -636,17 +636,18 @@ class Engine:
             dl = dlogits.permute(0, 2, 1).reshape(R, ncls)
         dl = dl.to(torch.float32).contiguous()
         # fc2
-        lib.call('x3d_small_gemm_ws', _ptr(dl), 1, ncls, _ptr(h1), F1, 1, self.g('fc2.weight'), F1, ncls, F1, R, None, 0,
-                 None, 1, self.head_ws.data_ptr(), self.head_ws.numel(), st)
-        lib.call('x3d_colsum', _ptr(dl), R, ncls, self.g('fc2.bias'), st)
+        # parameter gradients feed nothing downstream: side stream (K = batch rows: the plain tile kernel, no workspace)
+        self._wgrad('x3d_small_gemm', (dl, h1), _ptr(dl), 1, ncls, _ptr(h1), F1, 1, self.g('fc2.weight'), F1, ncls, F1, R,
+                    None, 0, None, 1)
+        self._wgrad('x3d_colsum', (dl,), _ptr(dl), R, ncls, self.g('fc2.bias'))
         dh = self._f32(R, F1)
         lib.call('x3d_small_gemm_ws', _ptr(dl), ncls, 1, self.p('fc2.weight'), F1, 1, _ptr(dh), F1, R, F1, ncls, None, 0,
                  None, 0, self.head_ws.data_ptr(), self.head_ws.numel(), st)
         dz = dh
         lib.call('x3d_relu_mask_mul', _ptr(dh), _ptr(h1), _ptr(dropout_mask), _ptr(dz), R * F1, st)
         # fc1
-        lib.call('x3d_small_gemm_ws', _ptr(dz), 1, F1, _ptr(pooled), C5, 1, self.g('fc1.weight'), C5, F1, C5, R, None, 0,
-                 None, 1, self.head_ws.data_ptr(), self.head_ws.numel(), st)
+        self._wgrad('x3d_small_gemm', (dz, pooled), _ptr(dz), 1, F1, _ptr(pooled), C5, 1, self.g('fc1.weight'), C5, F1, C5,
+                    R, None, 0, None, 1)
         dpooled = self._f32(R, C5)
         lib.call('x3d_small_gemm_ws', _ptr(dz), F1, 1, self.p('fc1.weight'), C5, 1, _ptr(dpooled), C5, R, C5, F1, None, 0,
                  None, 0, self.head_ws.data_ptr(), self.head_ws.numel(), st)
