@@ -16,6 +16,13 @@ python bench.py --version S --batch 16 --frames 13 --crop 160 --steps 10 --warmu
 echo "configs done"
 python tools/dw_microbench.py --json gpurun_out/${R}_dw_microbench.json > /dev/null 2>&1
 python tools/pw_microbench.py --json gpurun_out/${R}_pw_microbench.json > /dev/null 2>&1
+python tools/ew_microbench.py > gpurun_out/${R}_ew_microbench.jsonl 2>/dev/null
+python tools/head_gemm_microbench.py > gpurun_out/${R}_head_gemm_microbench.txt 2>&1
+python tools/head_gemm_microbench.py --rows 64 >> gpurun_out/${R}_head_gemm_microbench.txt 2>&1
+python tools/head_gemm_microbench.py --rows 256 >> gpurun_out/${R}_head_gemm_microbench.txt 2>&1
+python tools/marginal_cost.py --zero-input --json gpurun_out/${R}_marginal_cost.json > /dev/null 2>&1
+python tools/split_concurrency_probe.py > gpurun_out/${R}_split_concurrency_probe.txt 2>&1
+echo "microbenchmarks done"
 # launch list of the bench command (same command line ran above without ncu and exited 0)
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 5000 --csv --log-file gpurun_out/${R}_launches.csv \

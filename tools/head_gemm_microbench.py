@@ -66,8 +66,9 @@ def main():
         t1 = timed('x3d_small_gemm_ws', args[:-1] + (ws.data_ptr(), ws.numel(), st))
         tot[0] += t0
         tot[1] += t1
-        print(f'{name:34s} plain {t0:7.1f} us   split-K (ws) {t1:7.1f} us')
-    print(f'total plain {tot[0]:.1f} us, split-K {tot[1]:.1f} us   (an empty launch + two event records cost ~6 us here)')
+        print(f'{name:34s} x3d_small_gemm {t0:7.1f} us   x3d_small_gemm_ws {t1:7.1f} us')
+    print(f'total without workspace {tot[0]:.1f} us, with workspace (split-K where the dispatch picks it) {tot[1]:.1f} us   '
+          f'(an empty launch + two event records cost ~6 us here)')
 
 
 if __name__ == '__main__':
