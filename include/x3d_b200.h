@@ -265,6 +265,8 @@ typedef struct {
   float* momentum_buf;
   int64_t numel;
 } x3d_sgd_desc_t;
+/* one launch over all tensors (n_desc <= 2048): the work is cut into 4096-element blocks across the table, 16-byte
+ * accesses where the three pointers of a tensor are 16-byte aligned.  max_numel: largest numel of the table. */
 int x3d_sgd_step(const x3d_sgd_desc_t* descs_dev, int n_desc, int64_t max_numel, float lr,
                  float momentum, float weight_decay, float grad_scale, int first_step,
                  x3d_stream_t stream);
