@@ -16,9 +16,36 @@ namespace {
 
 constexpr int KT = 5;
 
+// Memory-level parallelism is what bounds these kernels: with one 16-byte load in flight per thread and ~120 registers
+// (2 CTAs/SM) an SM had ~12 KB outstanding -- 2.6 TB/s.  A thread now keeps the RAW 16-byte vectors of the KT window
+// planes plus LOOK planes of look-ahead in a register ring (plane p lives in slot (p + 2) % RING; the march is unrolled
+// over RING steps so every slot index is static and a loaded register is not touched before its plane is needed).
+constexpr int LOOK = 4;              // weight gradient: two rings (x and dy) next to the 5 x VEC accumulators
+constexpr int RING = KT + LOOK;
+constexpr int FLOOK = 6;             // forward / dgrad: one ring, deeper look-ahead (8 spills under the 128-register cap)
+constexpr int FRING = KT + FLOOK;
+
+template <typename T>
+__device__ __forceinline__ void unpack16(const uint4& q, float (&v)[Vec<T>::N]);
+template <>
+__device__ __forceinline__ void unpack16<float>(const uint4& q, float (&v)[4]) {
+  v[0] = __uint_as_float(q.x); v[1] = __uint_as_float(q.y); v[2] = __uint_as_float(q.z); v[3] = __uint_as_float(q.w);
+}
+template <>
+__device__ __forceinline__ void unpack16<__nv_bfloat16>(const uint4& q, float (&v)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <typename T>
+__device__ __forceinline__ uint4 ldg16(const T* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
 // block = cv channel vectors x rows positions; grid = (position chunks, N)
 template <typename T, bool FLIP, bool STATS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dw_temporal_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, int T_, int64_t P, int Cp,
                    int cv, int rows, double* __restrict__ stats) {
   x3d::pdl_prologue();
@@ -41,43 +68,41 @@ dw_temporal_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __re
     const int64_t plane = P * Cp;
     const T* xp = x + ((int64_t)n * T_ * P + p) * Cp + c0;
     T* yp = y + ((int64_t)n * T_ * P + p) * Cp + c0;
-    // window[k] = x[t + k - 2]; planes outside [0, T) are zero
-    float win[KT][VEC];
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);     // planes outside [0, T) are zero
+    uint4 ring[FRING];
 #pragma unroll
-    for (int k = 0; k < KT; ++k)
+    for (int i = 0; i < FRING; ++i) {
+      const int pl = i - KT / 2;
+      ring[i] = (pl >= 0 && pl < T_) ? ldg16(xp + (int64_t)pl * plane) : zero;
+    }
+    for (int t0 = 0; t0 < T_; t0 += FRING) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) win[k][j] = 0.f;
+      for (int s = 0; s < FRING; ++s) {
+        const int t = t0 + s;
+        if (t < T_) {
+          float o[VEC];
 #pragma unroll
-    for (int k = KT / 2; k < KT; ++k)
-      if (k - KT / 2 < T_) load_vec<T>(xp + (int64_t)(k - KT / 2) * plane, win[k]);
-    for (int t = 0; t < T_; ++t) {
-      float nxt[VEC];
+          for (int j = 0; j < VEC; ++j) o[j] = 0.f;
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) nxt[j] = 0.f;
-      if (t + KT / 2 + 1 < T_) load_vec<T>(xp + (int64_t)(t + KT / 2 + 1) * plane, nxt);   // needed by the NEXT output
-      float o[VEC];
+          for (int k = 0; k < KT; ++k) {
+            float v[VEC];
+            unpack16<T>(ring[(s + k) % FRING], v);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        float a = 0.f;
+            for (int j = 0; j < VEC; ++j) o[j] = fmaf(wk[k][j], v[j], o[j]);
+          }
+          store_vec<T>(yp + (int64_t)t * plane, o);
+          if (STATS) {
 #pragma unroll
-        for (int k = 0; k < KT; ++k) a = fmaf(wk[k][j], win[k][j], a);
-        o[j] = a;
-      }
-      store_vec<T>(yp + (int64_t)t * plane, o);
-      if (STATS) {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          const float r = round_to<T>(o[j]);
-          s1[j] += r;
-          s2[j] = fmaf(r, r, s2[j]);
+            for (int j = 0; j < VEC; ++j) {
+              const float r = round_to<T>(o[j]);
+              s1[j] += r;
+              s2[j] = fmaf(r, r, s2[j]);
+            }
+          }
+          const int pl = t - KT / 2 + FRING;            // plane t-2 retires, its slot takes plane t-2+FRING
+          ring[s] = pl < T_ ? ldg16(xp + (int64_t)pl * plane) : zero;
         }
       }
-#pragma unroll
-      for (int k = 0; k + 1 < KT; ++k)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) win[k][j] = win[k + 1][j];
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) win[KT - 1][j] = nxt[j];
     }
   }
   if (STATS) block_stats_flush<VEC>(s1, s2, cvec, Cp, s_acc, stats + (int64_t)n * Cp * 2);
@@ -85,7 +110,7 @@ dw_temporal_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __re
 
 // dw[c][k] += sum_{n,t,p} dy[n,t,p,c] * x[n, t + k - 2, p, c];  persistent blocks over (n, position chunk) units
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dw_temporal_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int T_, int64_t P,
                          int C, int Cp, int cv, int rows, int chunks, int64_t nunits) {
   x3d::pdl_prologue();
@@ -99,36 +124,41 @@ dw_temporal_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, floa
 #pragma unroll
     for (int j = 0; j < VEC; ++j) g[k][j] = 0.f;
   const int64_t plane = P * Cp;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
   for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
     const int n = (int)(u / chunks);
     const int64_t p = (u - (int64_t)n * chunks) * rows + prow;
     if (prow >= rows || p >= P) continue;
     const T* xp = x + ((int64_t)n * T_ * P + p) * Cp + c0;
     const T* dp = dy + ((int64_t)n * T_ * P + p) * Cp + c0;
-    float win[KT][VEC];
+    uint4 ring[RING], dring[LOOK];                 // x planes t-2 .. t+2+LOOK; dy planes t .. t+LOOK-1 (slot t % LOOK)
 #pragma unroll
-    for (int k = 0; k < KT; ++k)
+    for (int i = 0; i < RING; ++i) {
+      const int pl = i - KT / 2;
+      ring[i] = (pl >= 0 && pl < T_) ? ldg16(xp + (int64_t)pl * plane) : zero;
+    }
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) win[k][j] = 0.f;
+    for (int i = 0; i < LOOK; ++i) dring[i] = i < T_ ? ldg16(dp + (int64_t)i * plane) : zero;
+    // RING * LOOK is the common period of the two rings; the march is unrolled over it so all slot indices are static
+    for (int t0 = 0; t0 < T_; t0 += RING * LOOK) {
 #pragma unroll
-    for (int k = KT / 2; k < KT; ++k)
-      if (k - KT / 2 < T_) load_vec<T>(xp + (int64_t)(k - KT / 2) * plane, win[k]);
-    for (int t = 0; t < T_; ++t) {
-      float nxt[VEC], d[VEC];
+      for (int s = 0; s < RING * LOOK; ++s) {
+        const int t = t0 + s;
+        if (t < T_) {
+          float d[VEC];
+          unpack16<T>(dring[s % LOOK], d);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) nxt[j] = 0.f;
-      if (t + KT / 2 + 1 < T_) load_vec<T>(xp + (int64_t)(t + KT / 2 + 1) * plane, nxt);
-      load_vec<T>(dp + (int64_t)t * plane, d);
+          for (int k = 0; k < KT; ++k) {
+            float v[VEC];
+            unpack16<T>(ring[(s + k) % RING], v);
 #pragma unroll
-      for (int k = 0; k < KT; ++k)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) g[k][j] = fmaf(d[j], win[k][j], g[k][j]);
-#pragma unroll
-      for (int k = 0; k + 1 < KT; ++k)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) win[k][j] = win[k + 1][j];
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) win[KT - 1][j] = nxt[j];
+            for (int j = 0; j < VEC; ++j) g[k][j] = fmaf(d[j], v[j], g[k][j]);
+          }
+          const int pl = t - KT / 2 + RING;
+          ring[s % RING] = pl < T_ ? ldg16(xp + (int64_t)pl * plane) : zero;
+          dring[s % LOOK] = t + LOOK < T_ ? ldg16(dp + (int64_t)(t + LOOK) * plane) : zero;
+        }
+      }
     }
   }
   // block reduction without atomics: every thread parks its KT x VEC partials in its own row of shared memory,
