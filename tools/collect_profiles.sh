@@ -16,6 +16,7 @@ python bench.py --version S --batch 16 --frames 13 --crop 160 --steps 10 --warmu
 echo "configs done"
 python tools/dw_microbench.py --json gpurun_out/${R}_dw_microbench.json > /dev/null 2>&1
 python tools/pw_microbench.py --json gpurun_out/${R}_pw_microbench.json > /dev/null 2>&1
+python tools/stem_microbench.py > gpurun_out/${R}_stem_microbench.jsonl 2>/dev/null
 python tools/ew_microbench.py > gpurun_out/${R}_ew_microbench.jsonl 2>/dev/null
 python tools/head_gemm_microbench.py > gpurun_out/${R}_head_gemm_microbench.txt 2>&1
 python tools/head_gemm_microbench.py --rows 64 >> gpurun_out/${R}_head_gemm_microbench.txt 2>&1

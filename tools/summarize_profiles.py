@@ -16,7 +16,7 @@ os.makedirs(P, exist_ok=True)
 for name in ('bench.json', 'bench_reference.json', 'kernel_table.json', 'dw_microbench.json', 'pw_microbench.json', 'smi.csv',
              'multigrid_shapes.jsonl', 'bench_n2.json', 'bench_n4.json', 'bench_n8.json', 'fma_rate.txt', 'bench_xl.json', 'bench_s.json',
              'bench_multigrid.json', 'bench_charades.json', 'sass_mnemonics.txt', 'bench_xl_n8.json', 'bench_multigrid_n8.json',
-             'marginal_cost.json', 'head_gemm_microbench.txt', 'split_concurrency_probe.txt', 'ew_microbench.jsonl'):
+             'marginal_cost.json', 'stem_microbench.jsonl', 'pytest_gpu.log', 'head_gemm_microbench.txt', 'split_concurrency_probe.txt', 'ew_microbench.jsonl'):
     src = os.path.join(G, f'{R}_{name}')
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, f'{R}_{name}'))
