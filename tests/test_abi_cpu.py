@@ -27,6 +27,22 @@ def test_library_exports_every_declared_symbol():
     assert all(v == 0 for v in paths.values())
 
 
+def test_workspace_size_queries_are_host_only():
+    """the workspace-size entry points are plain host arithmetic (usable before any GPU work): head split-K scratch =
+    4 KB of tile tickets + slices x tiles x 16 KB, never more than the engine's fixed 16 MB for any multigrid batch"""
+    from x3d_multigrid_b200 import _lib
+    L = _lib.lib()
+    q = L.fn['x3d_small_gemm_workspace_bytes']
+    assert q(16, 400, 2048) == 4096 + 16 * 7 * 64 * 64 * 4          # fc2 forward: 7 column tiles, 16 slices of K
+    assert q(16, 2048, 432) == 4096 + 6 * 32 * 64 * 64 * 4          # fc1 forward: K / 64 = 6 slices
+    assert q(64, 2048, 16) == 4096 + 1 * 32 * 64 * 64 * 4           # K of one k-tile: no split
+    for rows in (1, 16, 64, 128, 256):
+        for n, k in ((2048, 432), (400, 2048), (432, 2048), (2048, 400)):
+            assert 4096 < q(rows, n, k) <= (16 << 20)
+    assert int(L.fn['x3d_pwconv_wgrad_workspace_bytes']()) >= (1 << 20)
+    assert L.launch_count() == 0
+
+
 def test_struct_layouts_match_header():
     from x3d_multigrid_b200 import _lib
     assert ctypes.sizeof(_lib.PackDesc) == 40
